@@ -1,0 +1,916 @@
+// C ABI of libbrickscore.so (include/brickscore.h): handle, resident catalog,
+// per-stream workspaces, scheduling of the scan units, and the entry points.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/brickscore.h"
+#include "bb_common.cuh"
+#include "bb_kernels.h"
+
+using namespace bb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p != nullptr) {
+      cudaError_t e = cudaFree(p);
+      p = nullptr;
+      cap = 0;
+      if (e != cudaSuccess) return e;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Workspace {
+  std::mutex mu;
+  DevBuf q_f32, q_bf16, cand, cand_cnt, thr_g, out_scores, out_ids, misc, stage, dump;
+  alignas(64) CUtensorMap tmap_q;
+  const void* tmap_q_ptr = nullptr;
+  int tmap_q_rows = 0;
+  int32_t* host_flag = nullptr;   // pinned
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct bb_handle {
+  bb_config cfg{};
+  int k_pad = 0;
+  int sm_count = 0;
+  int cta_group = 2;
+  bool loaded = false;
+  float* cat_f32 = nullptr;
+  __nv_bfloat16* cat_bf16 = nullptr;
+  int2* meta = nullptr;
+  int64_t* excl_off = nullptr;
+  int32_t* excl_ids = nullptr;
+  int64_t n_excl = 0;
+  uint32_t* theme_sets = nullptr;
+  int n_theme_sets = 0;
+  int theme_words = 32;
+  uint32_t* allow = nullptr;
+  bool allow_owned = false;
+  int n_allow = 0;
+  int64_t allow_words = 0;
+  alignas(64) CUtensorMap tmap_e;
+  bool tmap_e_ok = false;
+  EncodeTiledFn encode = nullptr;
+  std::mutex mu;
+  std::map<cudaStream_t, Workspace*> ws;
+  std::atomic<long long> launches{0};
+  std::atomic<long long> last_units{0};
+  unsigned long long* stat_dev = nullptr;
+  int32_t* err_dev = nullptr;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
+  double scan_ms = 0.0;
+  long long scan_launches = 0;
+  mutable std::mutex err_mu;
+  mutable std::string err;
+};
+
+namespace {
+
+int fail(const bb_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h != nullptr) {
+    std::lock_guard<std::mutex> g(h->err_mu);
+    h->err = buf;
+  } else {
+    g_create_error = buf;
+  }
+  return code;
+}
+
+#define BB_CUDA(h, expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(h, _e == cudaErrorMemoryAllocation ? BB_ERR_NOMEM : BB_ERR_CUDA, "%s: %s", #expr, \
+                  cudaGetErrorString(_e));                                                    \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  if (p == nullptr) return false;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// Returns a device view of `p` (`bytes` long): p itself when it is device memory,
+// else a staged copy inside `arena` (the arena must have been sized beforehand).
+struct Stager {
+  bb_handle* h;
+  DevBuf* buf;
+  size_t off = 0;
+  cudaStream_t stream;
+  size_t need = 0;
+  // pass 1: account
+  void account(const void* p, size_t bytes) {
+    if (p != nullptr && !is_device_ptr(p)) need += align256(bytes);
+  }
+  // pass 2: copy
+  cudaError_t get(const void* p, size_t bytes, const void** out) {
+    if (p == nullptr) { *out = nullptr; return cudaSuccess; }
+    if (is_device_ptr(p)) { *out = p; return cudaSuccess; }
+    void* d = static_cast<unsigned char*>(buf->p) + off;
+    off += align256(bytes);
+    *out = d;
+    return cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, stream);
+  }
+};
+
+Workspace* get_ws(bb_handle* h, cudaStream_t s) {
+  std::lock_guard<std::mutex> g(h->mu);
+  auto it = h->ws.find(s);
+  if (it != h->ws.end()) return it->second;
+  Workspace* w = new Workspace();
+  if (cudaMallocHost(reinterpret_cast<void**>(&w->host_flag), 64) != cudaSuccess) {
+    cudaGetLastError();
+    w->host_flag = nullptr;
+  }
+  h->ws[s] = w;
+  return w;
+}
+
+int make_tmap(bb_handle* h, CUtensorMap* out, const void* base, uint64_t rows, int k_pad, int box_rows) {
+  if (h->encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+      return fail(h, BB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_pad) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, BB_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+  return BB_OK;
+}
+
+struct Plan {
+  int n_qblocks, n_tiles, n_splits, n_groups, b_pad, tile_items;
+};
+
+Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
+  Plan p{};
+  const int rows = tc ? kTcRowsPerCta * h->cta_group : kFp32QRows;
+  p.tile_items = tc ? kTcTile : kFp32Tile;
+  p.b_pad = (n_queries + 255) / 256 * 256;
+  p.n_qblocks = (n_queries + rows - 1) / rows;
+  // every padded row must belong to a block so its candidate count is written
+  p.n_qblocks = p.b_pad / rows;
+  p.n_tiles = static_cast<int>((h->cfg.n_items + p.tile_items - 1) / p.tile_items);
+  if (p.n_tiles < 1) p.n_tiles = 1;
+  const int hw_groups = tc ? h->sm_count / h->cta_group : h->sm_count * 2;
+  const long long total = static_cast<long long>(p.n_qblocks) * p.n_tiles;
+  long long waves = total / (static_cast<long long>(hw_groups) * 8);
+  if (waves < 1) waves = 1;
+  if (waves > 16) waves = 16;
+  long long splits = (hw_groups * waves + p.n_qblocks - 1) / p.n_qblocks;
+  if (splits > p.n_tiles) splits = p.n_tiles;
+  if (splits < 1) splits = 1;
+  // bound candidate memory (2 KB per (split, row)) to 2 GiB
+  const long long max_splits = (2ll << 30) / (static_cast<long long>(p.b_pad) * kCap * 8);
+  if (splits > max_splits) splits = max_splits > 0 ? max_splits : 1;
+  p.n_splits = static_cast<int>(splits);
+  const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
+  p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
+  return p;
+}
+
+int device_guard(bb_handle* h) {
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return fail(h, BB_ERR_CUDA, "cudaSetDevice(%d): %s", h->cfg.device, cudaGetErrorString(e));
+  return BB_OK;
+}
+
+// Shared front half of bb_search / bb_debug_scores: stage inputs, build the query
+// operands, plan the units, run the scan.  On return `P` describes the candidate state.
+int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, float* dump, cudaStream_t stream,
+             ScanParams& P, Plan& plan) {
+  const int B = q->n_queries;
+  const int prec = q->precision;
+  const bool tc = prec != BB_PREC_FP32;
+  if (tc && h->cat_bf16 == nullptr) return fail(h, BB_ERR_STATE, "bf16 precision requested but BB_CFG_BUILD_BF16 not set");
+  if ((!tc || prec == BB_PREC_BF16_RESCORE) && h->cat_f32 == nullptr)
+    return fail(h, BB_ERR_STATE, "fp32 operands requested but BB_CFG_KEEP_FP32 not set");
+  if (tc && h->k_pad / 64 > kTcMaxKBlocks)
+    return fail(h, BB_ERR_UNSUPPORTED, "dim+cf_dim=%d exceeds the resident-operand limit of %d columns", h->k_pad,
+                kTcMaxKBlocks * 64);
+  if (q->q_emb == nullptr && q->q_item == nullptr && q->q_cf == nullptr)
+    return fail(h, BB_ERR_INVALID, "query batch has neither embeddings, item ids nor CF factors");
+  if ((q->q_emb != nullptr || q->q_item != nullptr) && h->cfg.dim == 0)
+    return fail(h, BB_ERR_INVALID, "content query given but catalog has dim=0");
+  if (q->q_cf != nullptr && h->cfg.cf_dim == 0) return fail(h, BB_ERR_INVALID, "CF query given but catalog has cf_dim=0");
+  if (q->n_constraints != 0 && q->n_constraints != 1 && q->n_constraints != B)
+    return fail(h, BB_ERR_INVALID, "n_constraints must be 0, 1 or n_queries");
+  if (q->n_constraints != 0 && q->constraints == nullptr) return fail(h, BB_ERR_INVALID, "constraints is NULL");
+
+  plan = make_plan(h, B, tc);
+  const int D = h->cfg.dim, F = h->cfg.cf_dim, KP = h->k_pad;
+
+  // ---- validate constraint indices on the host when the descriptors are host memory
+  if (q->n_constraints > 0 && !is_device_ptr(q->constraints)) {
+    for (int i = 0; i < q->n_constraints; ++i) {
+      const bb_constraint& c = q->constraints[i];
+      if (c.theme_set >= h->n_theme_sets) return fail(h, BB_ERR_INVALID, "constraint %d: theme_set %d out of range", i, c.theme_set);
+      if (c.allow_bitmap >= h->n_allow) return fail(h, BB_ERR_INVALID, "constraint %d: allow_bitmap %d out of range", i, c.allow_bitmap);
+      for (int e = 0; e < 3; ++e)
+        if (c.excl_list[e] >= h->n_excl) return fail(h, BB_ERR_INVALID, "constraint %d: excl_list %d out of range", i, c.excl_list[e]);
+    }
+  }
+
+  // ---- stage host inputs
+  Stager st{h, &w->stage, 0, stream, 0};
+  st.account(q->q_emb, sizeof(float) * B * D);
+  st.account(q->q_item, sizeof(int32_t) * B);
+  st.account(q->q_cf, sizeof(float) * B * F);
+  st.account(q->w_content, sizeof(float) * B);
+  st.account(q->w_cf, sizeof(float) * B);
+  st.account(q->constraints, sizeof(bb_constraint) * q->n_constraints);
+  st.account(q->self_id, sizeof(int32_t) * B);
+  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  const void *d_emb, *d_item, *d_cf, *d_wc, *d_wf, *d_cons, *d_self;
+  BB_CUDA(h, st.get(q->q_emb, sizeof(float) * B * D, &d_emb));
+  BB_CUDA(h, st.get(q->q_item, sizeof(int32_t) * B, &d_item));
+  BB_CUDA(h, st.get(q->q_cf, sizeof(float) * B * F, &d_cf));
+  BB_CUDA(h, st.get(q->w_content, sizeof(float) * B, &d_wc));
+  BB_CUDA(h, st.get(q->w_cf, sizeof(float) * B, &d_wf));
+  BB_CUDA(h, st.get(q->constraints, sizeof(bb_constraint) * q->n_constraints, &d_cons));
+  BB_CUDA(h, st.get(q->self_id, sizeof(int32_t) * B, &d_self));
+
+  // ---- query operands
+  const size_t qf_bytes = sizeof(float) * static_cast<size_t>(plan.b_pad) * KP;
+  const size_t qb_bytes = sizeof(__nv_bfloat16) * static_cast<size_t>(plan.b_pad) * KP;
+  BB_CUDA(h, w->q_f32.ensure(qf_bytes));
+  BB_CUDA(h, w->q_bf16.ensure(qb_bytes));
+  if (plan.b_pad > B) {
+    BB_CUDA(h, cudaMemsetAsync(static_cast<float*>(w->q_f32.p) + static_cast<size_t>(B) * KP, 0,
+                               sizeof(float) * static_cast<size_t>(plan.b_pad - B) * KP, stream));
+    BB_CUDA(h, cudaMemsetAsync(static_cast<__nv_bfloat16*>(w->q_bf16.p) + static_cast<size_t>(B) * KP, 0,
+                               sizeof(__nv_bfloat16) * static_cast<size_t>(plan.b_pad - B) * KP, stream));
+  }
+  BB_CUDA(h, cudaMemsetAsync(h->err_dev, 0, sizeof(int32_t), stream));
+  BB_CUDA(h, launch_prep_queries(static_cast<const float*>(d_emb), static_cast<const int32_t*>(d_item),
+                                 static_cast<const float*>(d_cf), static_cast<const float*>(d_wc),
+                                 static_cast<const float*>(d_wf), q->w_content_all, q->w_cf_all, B, D, F, KP,
+                                 h->cfg.metric, h->cat_f32, h->cat_bf16, h->cfg.id_offset, h->cfg.n_items,
+                                 static_cast<float*>(w->q_f32.p), w->q_bf16.p, h->err_dev, stream));
+  h->launches++;
+
+  // ---- candidate state
+  std::memset(&P, 0, sizeof(P));
+  P.n_items = h->cfg.n_items;
+  P.id_offset = h->cfg.id_offset;
+  P.meta = h->meta;
+  P.n_queries = B;
+  P.b_pad = plan.b_pad;
+  P.k_pad = KP;
+  P.k_sel = k_sel;
+  P.cons = static_cast<const bb_constraint*>(d_cons);
+  P.cons_stride = (q->n_constraints == B && B > 1) ? 1 : 0;
+  P.self_id = static_cast<const int32_t*>(d_self);
+  P.theme_sets = h->theme_sets;
+  P.theme_words = h->theme_words;
+  P.allow_bitmaps = h->allow;
+  P.allow_words = h->allow_words;
+  P.excl_off = h->excl_off;
+  P.excl_ids = h->excl_ids;
+  P.n_qblocks = plan.n_qblocks;
+  P.n_splits = plan.n_splits;
+  P.n_tiles = plan.n_tiles;
+  P.tile_items = plan.tile_items;
+  P.dump = dump;
+  P.stat_candidates = h->stat_dev;
+  P.err_flag = h->err_dev;
+  if (dump == nullptr) {
+    const size_t slots = static_cast<size_t>(plan.n_splits) * plan.b_pad;
+    BB_CUDA(h, w->cand.ensure(slots * kCap * sizeof(uint64_t)));
+    BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
+    BB_CUDA(h, w->thr_g.ensure(static_cast<size_t>(plan.b_pad) * sizeof(uint32_t)));
+    P.cand = static_cast<uint64_t*>(w->cand.p);
+    P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
+    P.thr_g = static_cast<uint32_t*>(w->thr_g.p);
+    BB_CUDA(h, launch_fill_u32(P.thr_g, kOrdNegInf, plan.b_pad, stream));
+    BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, sizeof(unsigned long long), stream));
+    h->launches++;
+  }
+
+  // ---- scan
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (h->profiling) {
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->prof_free.empty()) {
+      ev = h->prof_free.back();
+      h->prof_free.pop_back();
+    } else {
+      BB_CUDA(h, cudaEventCreate(&ev.first));
+      BB_CUDA(h, cudaEventCreate(&ev.second));
+    }
+  }
+  if (ev.first != nullptr) BB_CUDA(h, cudaEventRecord(ev.first, stream));
+  if (tc) {
+    if (w->tmap_q_ptr != w->q_bf16.p || w->tmap_q_rows != plan.b_pad) {
+      int rc = make_tmap(h, &w->tmap_q, w->q_bf16.p, static_cast<uint64_t>(plan.b_pad), KP, kTcRowsPerCta);
+      if (rc != BB_OK) return rc;
+      w->tmap_q_ptr = w->q_bf16.p;
+      w->tmap_q_rows = plan.b_pad;
+    }
+    if (!h->tmap_e_ok) {
+      int rc = make_tmap(h, &h->tmap_e, h->cat_bf16, static_cast<uint64_t>(h->cfg.n_items), KP, kTcTile / h->cta_group);
+      if (rc != BB_OK) return rc;
+      h->tmap_e_ok = true;
+    }
+    BB_CUDA(h, launch_scan_tc(P, &w->tmap_q, &h->tmap_e, h->cta_group, plan.n_groups, stream));
+  } else {
+    BB_CUDA(h, launch_scan_fp32(P, static_cast<const float*>(w->q_f32.p), h->cat_f32, stream));
+  }
+  if (ev.first != nullptr) {
+    BB_CUDA(h, cudaEventRecord(ev.second, stream));
+    std::lock_guard<std::mutex> g(h->mu);
+    h->prof_pending.push_back(ev);
+  }
+  h->launches++;
+  h->last_units = static_cast<long long>(plan.n_qblocks) * plan.n_splits;
+  return BB_OK;
+}
+
+int check_device_flag(bb_handle* h, Workspace* w, cudaStream_t stream) {
+  int32_t flag = 0;
+  if (w->host_flag != nullptr) {
+    BB_CUDA(h, cudaMemcpyAsync(w->host_flag, h->err_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    BB_CUDA(h, cudaStreamSynchronize(stream));
+    flag = *w->host_flag;
+  } else {
+    BB_CUDA(h, cudaMemcpyAsync(&flag, h->err_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    BB_CUDA(h, cudaStreamSynchronize(stream));
+  }
+  if (flag == 1) return fail(h, BB_ERR_INVALID, "q_item / id outside this shard's id range");
+  if (flag != 0) return fail(h, BB_ERR_CUDA, "device watchdog code %d", flag);
+  return BB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char* bb_version(void) { return "brickscore 0.1.0 (sm_100a)"; }
+
+const char* bb_last_error(const bb_handle* h) {
+  if (h == nullptr) return g_create_error.c_str();
+  std::lock_guard<std::mutex> g(h->err_mu);
+  thread_local std::string copy;
+  copy = h->err;
+  return copy.c_str();
+}
+
+int bb_create(bb_handle** out, const bb_config* cfg) {
+  if (out == nullptr || cfg == nullptr) return fail(nullptr, BB_ERR_INVALID, "bb_create: NULL argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(bb_config)) return fail(nullptr, BB_ERR_INVALID, "bb_config.struct_size mismatch");
+  if (cfg->n_items < 0 || cfg->dim < 0 || cfg->cf_dim < 0) return fail(nullptr, BB_ERR_INVALID, "negative shape");
+  if (cfg->n_items > 0 && cfg->dim + cfg->cf_dim <= 0) return fail(nullptr, BB_ERR_INVALID, "dim + cf_dim must be > 0");
+  if (cfg->k_max < 0 || cfg->k_max > kMaxSel) return fail(nullptr, BB_ERR_UNSUPPORTED, "k_max must be in [0, %d]", kMaxSel);
+  if (cfg->n_items + cfg->id_offset > 0x7fffffffll) return fail(nullptr, BB_ERR_UNSUPPORTED, "ids must fit int32");
+  if (cfg->theme_bits < 0 || cfg->theme_bits % 32 != 0) return fail(nullptr, BB_ERR_INVALID, "theme_bits must be a multiple of 32");
+  if (cfg->metric != BB_METRIC_COSINE && cfg->metric != BB_METRIC_IP) return fail(nullptr, BB_ERR_INVALID, "unknown metric");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, BB_ERR_CUDA, "no CUDA device (%s); brickscore has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, BB_ERR_INVALID, "device %d out of range", cfg->device);
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, BB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop{};
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, BB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, BB_ERR_UNSUPPORTED, "device is sm_%d%d; brickscore is built for sm_100a only", prop.major, prop.minor);
+
+  bb_handle* h = new bb_handle();
+  h->cfg = *cfg;
+  if (h->cfg.flags == 0) h->cfg.flags = BB_CFG_KEEP_FP32 | BB_CFG_BUILD_BF16;
+  if (h->cfg.theme_bits == 0) h->cfg.theme_bits = 1024;
+  h->theme_words = h->cfg.theme_bits / 32;
+  h->k_pad = (cfg->dim + cfg->cf_dim + 63) / 64 * 64;
+  if (h->k_pad == 0) h->k_pad = 64;
+  h->sm_count = prop.multiProcessorCount;
+  const char* cg = getenv("BB_CTA_GROUP");
+  h->cta_group = (cg != nullptr && atoi(cg) == 1) ? 1 : 2;
+  auto bail = [&](int code) { bb_destroy(h); return code; };
+  const size_t rows = static_cast<size_t>(cfg->n_items);
+  if (rows > 0) {
+    if (h->cfg.flags & BB_CFG_KEEP_FP32) {
+      e = cudaMalloc(reinterpret_cast<void**>(&h->cat_f32), rows * h->k_pad * sizeof(float));
+      if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "fp32 catalog alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+    }
+    if (h->cfg.flags & BB_CFG_BUILD_BF16) {
+      e = cudaMalloc(reinterpret_cast<void**>(&h->cat_bf16), rows * h->k_pad * sizeof(__nv_bfloat16));
+      if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "bf16 catalog alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+    }
+    e = cudaMalloc(reinterpret_cast<void**>(&h->meta), rows * sizeof(int2));
+    if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "metadata alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+  }
+  e = cudaMalloc(reinterpret_cast<void**>(&h->stat_dev), 64);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->err_dev), 64);
+  if (e == cudaSuccess) e = cudaMemset(h->stat_dev, 0, 64);
+  if (e == cudaSuccess) e = cudaMemset(h->err_dev, 0, 64);
+  if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "flag alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+  *out = h;
+  return BB_OK;
+}
+
+void bb_destroy(bb_handle* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->ws) {
+    Workspace* w = kv.second;
+    for (DevBuf* b : {&w->q_f32, &w->q_bf16, &w->cand, &w->cand_cnt, &w->thr_g, &w->out_scores, &w->out_ids, &w->misc,
+                      &w->stage, &w->dump})
+      b->release();
+    if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
+    delete w;
+  }
+  if (h->cat_f32) cudaFree(h->cat_f32);
+  if (h->cat_bf16) cudaFree(h->cat_bf16);
+  if (h->meta) cudaFree(h->meta);
+  if (h->excl_off) cudaFree(h->excl_off);
+  if (h->excl_ids) cudaFree(h->excl_ids);
+  if (h->theme_sets) cudaFree(h->theme_sets);
+  if (h->allow && h->allow_owned) cudaFree(h->allow);
+  for (auto* v : {&h->prof_pending, &h->prof_free})
+    for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  if (h->stat_dev) cudaFree(h->stat_dev);
+  if (h->err_dev) cudaFree(h->err_dev);
+  cudaGetLastError();
+  delete h;
+}
+
+int bb_get_info(const bb_handle* hc, bb_info* info) {
+  bb_handle* h = const_cast<bb_handle*>(hc);
+  if (h == nullptr || info == nullptr) return BB_ERR_INVALID;
+  if (info->struct_size != sizeof(bb_info)) return fail(h, BB_ERR_INVALID, "bb_info.struct_size mismatch");
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  info->sm_count = h->sm_count;
+  info->k_pad = h->k_pad;
+  info->cta_group = h->cta_group;
+  info->launches = h->launches.load();
+  info->last_units = h->last_units.load();
+  unsigned long long c = 0;
+  BB_CUDA(h, cudaMemcpy(&c, h->stat_dev, sizeof(c), cudaMemcpyDeviceToHost));
+  info->last_candidates = static_cast<int64_t>(c);
+  const double rows = static_cast<double>(h->cfg.n_items);
+  info->bytes_fp32 = h->cat_f32 ? rows * h->k_pad * 4.0 : 0.0;
+  info->bytes_bf16 = h->cat_bf16 ? rows * h->k_pad * 2.0 : 0.0;
+  {
+    std::lock_guard<std::mutex> g(h->mu);
+    for (auto& ev : h->prof_pending) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+        h->scan_ms += ms;
+        h->scan_launches++;
+      }
+      h->prof_free.push_back(ev);
+    }
+    h->prof_pending.clear();
+    cudaGetLastError();
+  }
+  info->scan_ms = h->scan_ms;
+  info->scan_launches = h->scan_launches;
+  return BB_OK;
+}
+
+int bb_set_profiling(bb_handle* h, int enable) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  std::lock_guard<std::mutex> g(h->mu);
+  for (auto& ev : h->prof_pending) {
+    cudaEventSynchronize(ev.second);
+    h->prof_free.push_back(ev);
+  }
+  h->prof_pending.clear();
+  h->profiling = enable != 0;
+  h->scan_ms = 0.0;
+  h->scan_launches = 0;
+  return BB_OK;
+}
+
+int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float* emb, const float* item_factors,
+                    const int32_t* num_parts, const int16_t* year, const int16_t* theme_id, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (row_begin < 0 || n_rows < 0 || row_begin + n_rows > h->cfg.n_items) return fail(h, BB_ERR_INVALID, "row range outside catalog");
+  if (h->cfg.dim > 0 && emb == nullptr) return fail(h, BB_ERR_INVALID, "emb is NULL but dim=%d", h->cfg.dim);
+  if (h->cfg.cf_dim > 0 && item_factors == nullptr) return fail(h, BB_ERR_INVALID, "item_factors is NULL but cf_dim=%d", h->cfg.cf_dim);
+  const int D = h->cfg.dim, F = h->cfg.cf_dim, KP = h->k_pad;
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  const int64_t chunk = 1 << 18;   // staging granularity for host inputs
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+    const int64_t n = (n_rows - r0 < chunk) ? (n_rows - r0) : chunk;
+    Stager st{h, &w->stage, 0, stream, 0};
+    const float* e_p = emb ? emb + r0 * D : nullptr;
+    const float* f_p = item_factors ? item_factors + r0 * F : nullptr;
+    const int32_t* p_p = num_parts ? num_parts + r0 : nullptr;
+    const int16_t* y_p = year ? year + r0 : nullptr;
+    const int16_t* t_p = theme_id ? theme_id + r0 : nullptr;
+    st.account(e_p, sizeof(float) * n * D);
+    st.account(f_p, sizeof(float) * n * F);
+    st.account(p_p, sizeof(int32_t) * n);
+    st.account(y_p, sizeof(int16_t) * n);
+    st.account(t_p, sizeof(int16_t) * n);
+    if (st.need > 0) {
+      if (w->stage.cap < st.need + 256) BB_CUDA(h, cudaStreamSynchronize(stream));   // previous chunk still reading it
+      BB_CUDA(h, w->stage.ensure(st.need + 256));
+    }
+    const void *de, *df, *dp, *dy, *dt;
+    BB_CUDA(h, st.get(e_p, sizeof(float) * n * D, &de));
+    BB_CUDA(h, st.get(f_p, sizeof(float) * n * F, &df));
+    BB_CUDA(h, st.get(p_p, sizeof(int32_t) * n, &dp));
+    BB_CUDA(h, st.get(y_p, sizeof(int16_t) * n, &dy));
+    BB_CUDA(h, st.get(t_p, sizeof(int16_t) * n, &dt));
+    const int64_t row = row_begin + r0;
+    BB_CUDA(h, launch_prep_catalog(static_cast<const float*>(de), static_cast<const float*>(df), n, D, F, KP,
+                                   h->cfg.metric, h->cat_f32 ? h->cat_f32 + row * KP : nullptr,
+                                   h->cat_bf16 ? h->cat_bf16 + row * KP : nullptr, stream));
+    BB_CUDA(h, launch_pack_meta(static_cast<const int32_t*>(dp), static_cast<const int16_t*>(dy),
+                                static_cast<const int16_t*>(dt), n, h->meta + row, stream));
+    h->launches += 2;
+    if (st.need > 0) BB_CUDA(h, cudaStreamSynchronize(stream));   // staging buffer is reused by the next chunk
+  }
+  h->loaded = true;
+  return BB_OK;
+}
+
+int bb_fetch_embeddings(bb_handle* h, int32_t n, const int32_t* ids, float* out, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
+  if (n <= 0 || ids == nullptr || out == nullptr) return fail(h, BB_ERR_INVALID, "bad arguments");
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  Stager st{h, &w->stage, 0, stream, 0};
+  st.account(ids, sizeof(int32_t) * n);
+  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  const void* d_ids;
+  BB_CUDA(h, st.get(ids, sizeof(int32_t) * n, &d_ids));
+  const bool out_dev = is_device_ptr(out);
+  float* d_out = out;
+  if (!out_dev) {
+    BB_CUDA(h, w->misc.ensure(sizeof(float) * static_cast<size_t>(n) * h->cfg.dim));
+    d_out = static_cast<float*>(w->misc.p);
+  }
+  BB_CUDA(h, cudaMemsetAsync(h->err_dev, 0, sizeof(int32_t), stream));
+  BB_CUDA(h, launch_gather_rows(h->cat_f32, h->cat_bf16, h->k_pad, h->cfg.dim, h->cfg.id_offset, h->cfg.n_items,
+                                static_cast<const int32_t*>(d_ids), n, d_out, h->err_dev, stream));
+  h->launches++;
+  if (!out_dev) {
+    BB_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * static_cast<size_t>(n) * h->cfg.dim, cudaMemcpyDeviceToHost, stream));
+    return check_device_flag(h, w, stream);
+  }
+  return BB_OK;
+}
+
+static int replace_table(bb_handle* h, void** slot, const void* src, size_t bytes) {
+  if (*slot != nullptr) {
+    BB_CUDA(h, cudaDeviceSynchronize());
+    BB_CUDA(h, cudaFree(*slot));
+    *slot = nullptr;
+  }
+  if (bytes == 0) return BB_OK;
+  BB_CUDA(h, cudaMalloc(slot, bytes));
+  BB_CUDA(h, cudaMemcpy(*slot, src, bytes, cudaMemcpyDefault));
+  return BB_OK;
+}
+
+int bb_set_exclusion_lists(bb_handle* h, int64_t n_lists, const int64_t* offsets, const int32_t* item_ids) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_lists < 0 || (n_lists > 0 && offsets == nullptr)) return fail(h, BB_ERR_INVALID, "bad exclusion lists");
+  int64_t total = 0;
+  if (n_lists > 0) {
+    if (is_device_ptr(offsets)) BB_CUDA(h, cudaMemcpy(&total, offsets + n_lists, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    else total = offsets[n_lists];
+  }
+  if (total > 0 && item_ids == nullptr) return fail(h, BB_ERR_INVALID, "item_ids is NULL");
+  rc = replace_table(h, reinterpret_cast<void**>(&h->excl_off), offsets, n_lists > 0 ? sizeof(int64_t) * (n_lists + 1) : 0);
+  if (rc != BB_OK) return rc;
+  rc = replace_table(h, reinterpret_cast<void**>(&h->excl_ids), item_ids, sizeof(int32_t) * total);
+  if (rc != BB_OK) return rc;
+  h->n_excl = n_lists;
+  return BB_OK;
+}
+
+int bb_set_theme_sets(bb_handle* h, int32_t n_sets, const uint32_t* bitmaps) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_sets < 0 || (n_sets > 0 && bitmaps == nullptr)) return fail(h, BB_ERR_INVALID, "bad theme sets");
+  rc = replace_table(h, reinterpret_cast<void**>(&h->theme_sets), bitmaps, sizeof(uint32_t) * static_cast<size_t>(n_sets) * h->theme_words);
+  if (rc != BB_OK) return rc;
+  h->n_theme_sets = n_sets;
+  return BB_OK;
+}
+
+int bb_set_allow_bitmaps(bb_handle* h, int32_t n_bitmaps, const uint32_t* bitmaps) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_bitmaps < 0 || (n_bitmaps > 0 && bitmaps == nullptr)) return fail(h, BB_ERR_INVALID, "bad allow bitmaps");
+  const int64_t words = (h->cfg.n_items + 31) / 32;
+  if (h->allow != nullptr && !h->allow_owned) h->allow = nullptr;
+  rc = replace_table(h, reinterpret_cast<void**>(&h->allow), bitmaps, sizeof(uint32_t) * static_cast<size_t>(n_bitmaps) * words);
+  if (rc != BB_OK) return rc;
+  h->allow_owned = true;
+  h->n_allow = n_bitmaps;
+  h->allow_words = words;
+  return BB_OK;
+}
+
+int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (q == nullptr || out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  if (q->struct_size != sizeof(bb_query_batch)) return fail(h, BB_ERR_INVALID, "bb_query_batch.struct_size mismatch");
+  if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
+  if (q->n_queries <= 0) return fail(h, BB_ERR_INVALID, "n_queries must be > 0");
+  if (h->cfg.max_batch > 0 && q->n_queries > h->cfg.max_batch) return fail(h, BB_ERR_INVALID, "n_queries %d > max_batch %d", q->n_queries, h->cfg.max_batch);
+  if (k <= 0 || k > kMaxSel || (h->cfg.k_max > 0 && k > h->cfg.k_max)) return fail(h, BB_ERR_INVALID, "k=%d outside [1, %d]", k, h->cfg.k_max > 0 ? h->cfg.k_max : kMaxSel);
+  if (q->precision < BB_PREC_FP32 || q->precision > BB_PREC_BF16_RESCORE) return fail(h, BB_ERR_INVALID, "unknown precision");
+
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
+  // k' kept per candidate buffer: a multiple of 32; the re-scored path over-fetches.
+  int k_sel = (k + 31) / 32 * 32;
+  if (rescore) {
+    k_sel = (k + k / 4 + 8 + 31) / 32 * 32;
+    if (k_sel > kMaxSel) k_sel = kMaxSel;
+  }
+  ScanParams P;
+  Plan plan;
+  rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan);
+  if (rc != BB_OK) return rc;
+
+  const int B = q->n_queries;
+  const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
+  float* d_scores = out_scores;
+  int32_t* d_ids = out_ids;
+  if (!s_dev) {
+    BB_CUDA(h, w->out_scores.ensure(sizeof(float) * static_cast<size_t>(B) * k));
+    d_scores = static_cast<float*>(w->out_scores.p);
+  }
+  if (!i_dev) {
+    BB_CUDA(h, w->out_ids.ensure(sizeof(int32_t) * static_cast<size_t>(B) * k));
+    d_ids = static_cast<int32_t*>(w->out_ids.p);
+  }
+  BB_CUDA(h, launch_merge_emit(P, k, rescore, static_cast<const float*>(w->q_f32.p), h->cat_f32,
+                               (q->flags & BB_Q_SCORES_AS_L2) != 0, d_scores, d_ids, stream));
+  h->launches++;
+  if (!s_dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d_scores, sizeof(float) * static_cast<size_t>(B) * k, cudaMemcpyDeviceToHost, stream));
+  if (!i_dev) BB_CUDA(h, cudaMemcpyAsync(out_ids, d_ids, sizeof(int32_t) * static_cast<size_t>(B) * k, cudaMemcpyDeviceToHost, stream));
+  if (!s_dev || !i_dev) return check_device_flag(h, w, stream);
+  return BB_OK;
+}
+
+int bb_debug_scores(bb_handle* h, const bb_query_batch* q, float* out_scores, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (q == nullptr || out_scores == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  if (q->struct_size != sizeof(bb_query_batch)) return fail(h, BB_ERR_INVALID, "bb_query_batch.struct_size mismatch");
+  if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
+  if (q->n_queries <= 0) return fail(h, BB_ERR_INVALID, "n_queries must be > 0");
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  const size_t bytes = sizeof(float) * static_cast<size_t>(q->n_queries) * h->cfg.n_items;
+  const bool dev = is_device_ptr(out_scores);
+  float* d = out_scores;
+  if (!dev) {
+    BB_CUDA(h, w->dump.ensure(bytes));
+    d = static_cast<float*>(w->dump.p);
+  }
+  ScanParams P;
+  Plan plan;
+  rc = run_scan(h, w, q, 32, d, stream, P, plan);
+  if (rc != BB_OK) return rc;
+  if (!dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d, bytes, cudaMemcpyDeviceToHost, stream));
+  return check_device_flag(h, w, stream);
+}
+
+int bb_apply_constraints(bb_handle* h, const bb_constraint* constraints, int32_t n, uint32_t* out_bitmaps,
+                         int64_t* out_counts, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
+  if (n <= 0 || constraints == nullptr || out_bitmaps == nullptr) return fail(h, BB_ERR_INVALID, "bad arguments");
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  const int64_t words = (h->cfg.n_items + 31) / 32;
+  Stager st{h, &w->stage, 0, stream, 0};
+  st.account(constraints, sizeof(bb_constraint) * n);
+  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  const void* d_cons;
+  BB_CUDA(h, st.get(constraints, sizeof(bb_constraint) * n, &d_cons));
+  const bool b_dev = is_device_ptr(out_bitmaps);
+  const size_t bm_bytes = sizeof(uint32_t) * static_cast<size_t>(n) * words;
+  BB_CUDA(h, w->misc.ensure((b_dev ? 0 : align256(bm_bytes)) + sizeof(unsigned long long) * n + 256));
+  uint32_t* d_bm = b_dev ? out_bitmaps : static_cast<uint32_t*>(w->misc.p);
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(w->misc.p) + (b_dev ? 0 : align256(bm_bytes)));
+  BB_CUDA(h, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * n, stream));
+  ScanParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.n_items = h->cfg.n_items;
+  P.id_offset = h->cfg.id_offset;
+  P.meta = h->meta;
+  P.cons = static_cast<const bb_constraint*>(d_cons);
+  P.theme_sets = h->theme_sets;
+  P.theme_words = h->theme_words;
+  P.allow_bitmaps = h->allow;
+  P.allow_words = h->allow_words;
+  P.excl_off = h->excl_off;
+  P.excl_ids = h->excl_ids;
+  BB_CUDA(h, launch_mask(P, n, d_bm, d_cnt, stream));
+  h->launches++;
+  if (!b_dev) BB_CUDA(h, cudaMemcpyAsync(out_bitmaps, d_bm, bm_bytes, cudaMemcpyDeviceToHost, stream));
+  if (out_counts != nullptr)
+    BB_CUDA(h, cudaMemcpyAsync(out_counts, d_cnt, sizeof(int64_t) * n, is_device_ptr(out_counts) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+  if (!b_dev || (out_counts != nullptr && !is_device_ptr(out_counts))) BB_CUDA(h, cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+int bb_hybrid_combine(bb_handle* h, int32_t n_rows, int32_t len_c, const int32_t* c_ids, const float* c_scores,
+                      int32_t len_f, const int32_t* f_ids, const float* f_scores, const double* weights,
+                      int32_t weights_per_row, int32_t k, double* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_rows <= 0 || k <= 0 || len_c < 0 || len_f < 0 || len_c + len_f > 512 || len_c + len_f == 0)
+    return fail(h, BB_ERR_INVALID, "hybrid_combine: bad shape (len_c + len_f must be in [1, 512])");
+  if (weights == nullptr || out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  if ((len_c > 0 && (c_ids == nullptr || c_scores == nullptr)) || (len_f > 0 && (f_ids == nullptr || f_scores == nullptr)))
+    return fail(h, BB_ERR_INVALID, "NULL list");
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  Stager st{h, &w->stage, 0, stream, 0};
+  const size_t nc = static_cast<size_t>(n_rows) * len_c, nf = static_cast<size_t>(n_rows) * len_f;
+  const size_t nw = weights_per_row ? static_cast<size_t>(n_rows) * 2 : 2;
+  st.account(c_ids, 4 * nc); st.account(c_scores, 4 * nc); st.account(f_ids, 4 * nf); st.account(f_scores, 4 * nf);
+  st.account(weights, 8 * nw);
+  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  const void *dci, *dcs, *dfi, *dfs, *dw;
+  BB_CUDA(h, st.get(c_ids, 4 * nc, &dci)); BB_CUDA(h, st.get(c_scores, 4 * nc, &dcs));
+  BB_CUDA(h, st.get(f_ids, 4 * nf, &dfi)); BB_CUDA(h, st.get(f_scores, 4 * nf, &dfs));
+  BB_CUDA(h, st.get(weights, 8 * nw, &dw));
+  const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
+  const size_t so = align256(sizeof(double) * static_cast<size_t>(n_rows) * k);
+  BB_CUDA(h, w->misc.ensure(so + sizeof(int32_t) * static_cast<size_t>(n_rows) * k + 256));
+  double* d_s = s_dev ? out_scores : static_cast<double*>(w->misc.p);
+  int32_t* d_i = i_dev ? out_ids : reinterpret_cast<int32_t*>(static_cast<unsigned char*>(w->misc.p) + so);
+  BB_CUDA(h, launch_hybrid_combine(n_rows, len_c, static_cast<const int32_t*>(dci), static_cast<const float*>(dcs), len_f,
+                                   static_cast<const int32_t*>(dfi), static_cast<const float*>(dfs),
+                                   static_cast<const double*>(dw), weights_per_row ? 1 : 0, k, d_s, d_i, stream));
+  h->launches++;
+  if (!s_dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d_s, sizeof(double) * static_cast<size_t>(n_rows) * k, cudaMemcpyDeviceToHost, stream));
+  if (!i_dev) BB_CUDA(h, cudaMemcpyAsync(out_ids, d_i, sizeof(int32_t) * static_cast<size_t>(n_rows) * k, cudaMemcpyDeviceToHost, stream));
+  if (!s_dev || !i_dev) BB_CUDA(h, cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+int bb_merge_topk(bb_handle* h, int32_t n_queries, int32_t n_lists, int32_t len, const float* scores,
+                  const int32_t* ids, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_queries <= 0 || n_lists <= 0 || len <= 0 || k <= 0 || k > kMaxSel) return fail(h, BB_ERR_INVALID, "merge_topk: bad shape");
+  if (scores == nullptr || ids == nullptr || out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  const size_t n_in = static_cast<size_t>(n_lists) * n_queries * len;
+  Stager st{h, &w->stage, 0, stream, 0};
+  st.account(scores, 4 * n_in); st.account(ids, 4 * n_in);
+  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  const void *ds, *di;
+  BB_CUDA(h, st.get(scores, 4 * n_in, &ds)); BB_CUDA(h, st.get(ids, 4 * n_in, &di));
+  const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
+  const size_t n_out = static_cast<size_t>(n_queries) * k;
+  if (!s_dev) BB_CUDA(h, w->out_scores.ensure(4 * n_out));
+  if (!i_dev) BB_CUDA(h, w->out_ids.ensure(4 * n_out));
+  float* d_s = s_dev ? out_scores : static_cast<float*>(w->out_scores.p);
+  int32_t* d_i = i_dev ? out_ids : static_cast<int32_t*>(w->out_ids.p);
+  BB_CUDA(h, launch_merge_lists(n_queries, n_lists, len, static_cast<const float*>(ds), static_cast<const int32_t*>(di), k, d_s, d_i, stream));
+  h->launches++;
+  if (!s_dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d_s, 4 * n_out, cudaMemcpyDeviceToHost, stream));
+  if (!i_dev) BB_CUDA(h, cudaMemcpyAsync(out_ids, d_i, 4 * n_out, cudaMemcpyDeviceToHost, stream));
+  if (!s_dev || !i_dev) BB_CUDA(h, cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+int bb_item_item_topk(bb_handle* h, int64_t n_users, int32_t n_items, const int64_t* indptr, const int32_t* indices,
+                      const float* values, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_users <= 0 || n_items <= 1 || k <= 0 || k > kMaxSel || k >= n_items) return fail(h, BB_ERR_INVALID, "item_item: bad shape");
+  if (indptr == nullptr || indices == nullptr || values == nullptr || out_scores == nullptr || out_ids == nullptr)
+    return fail(h, BB_ERR_INVALID, "NULL argument");
+  Workspace* w = get_ws(h, stream);
+  std::lock_guard<std::mutex> g(w->mu);
+  int64_t nnz = 0;
+  if (is_device_ptr(indptr)) BB_CUDA(h, cudaMemcpy(&nnz, indptr + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  else nnz = indptr[n_users];
+  if (nnz < 0) return fail(h, BB_ERR_INVALID, "negative nnz");
+  Stager st{h, &w->stage, 0, stream, 0};
+  st.account(indptr, 8 * static_cast<size_t>(n_users + 1)); st.account(indices, 4 * static_cast<size_t>(nnz)); st.account(values, 4 * static_cast<size_t>(nnz));
+  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  const void *dp, *di, *dv;
+  BB_CUDA(h, st.get(indptr, 8 * static_cast<size_t>(n_users + 1), &dp));
+  BB_CUDA(h, st.get(indices, 4 * static_cast<size_t>(nnz), &di));
+  BB_CUDA(h, st.get(values, 4 * static_cast<size_t>(nnz), &dv));
+  const size_t ws_bytes = item_item_workspace_bytes(n_users, n_items, nnz);
+  BB_CUDA(h, w->misc.ensure(ws_bytes));
+  const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
+  const size_t n_out = static_cast<size_t>(n_items) * k;
+  if (!s_dev) BB_CUDA(h, w->out_scores.ensure(4 * n_out));
+  if (!i_dev) BB_CUDA(h, w->out_ids.ensure(4 * n_out));
+  float* d_s = s_dev ? out_scores : static_cast<float*>(w->out_scores.p);
+  int32_t* d_i = i_dev ? out_ids : static_cast<int32_t*>(w->out_ids.p);
+  int n_launch = 0;
+  BB_CUDA(h, launch_item_item(n_users, n_items, static_cast<const int64_t*>(dp), static_cast<const int32_t*>(di),
+                              static_cast<const float*>(dv), k, d_s, d_i, w->misc.p, w->misc.cap, stream, &n_launch));
+  h->launches += n_launch;
+  if (!s_dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d_s, 4 * n_out, cudaMemcpyDeviceToHost, stream));
+  if (!i_dev) BB_CUDA(h, cudaMemcpyAsync(out_ids, d_i, 4 * n_out, cudaMemcpyDeviceToHost, stream));
+  if (!s_dev || !i_dev) BB_CUDA(h, cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+// Bandwidth kernels around the scan: operand preparation (K2), constraint mask
+// (K3), candidate merge / exact re-score / emit (K4 + K6), cross-shard list merge
+// and the reference-semantics hybrid combine (K5).  All are HBM- or latency-bound
+// integer / fp32 work: coalesced 128-bit accesses, one warp per row or per query.
+#include <cuda_bf16.h>
+
+#include "bb_common.cuh"
+#include "bb_kernels.h"
+
+namespace bb {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ K2: catalog rows
+// One warp per row: L2 norm of the embedding part (sklearn normalize semantics:
+// zero rows are divided by 1, recommendation_system.py:214), write
+// [e_hat | v | 0-pad] as fp32 and bf16.
+__global__ void __launch_bounds__(256)
+prep_catalog_kernel(const float* __restrict__ emb, const float* __restrict__ cf, int64_t n_rows, int dim, int cf_dim,
+                    int k_pad, int metric, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  float inv_norm_den = 1.f;
+  if (dim > 0 && metric == BB_METRIC_COSINE) {
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+      const float x = __ldg(emb + row * dim + c);
+      ss = fmaf(x, x, ss);
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    inv_norm_den = (nrm == 0.f) ? 1.f : nrm;
+  }
+  for (int c = lane; c < k_pad; c += 32) {
+    float x = 0.f;
+    if (c < dim) x = __fdiv_rn(__ldg(emb + row * dim + c), inv_norm_den);
+    else if (c < dim + cf_dim) x = __ldg(cf + row * cf_dim + (c - dim));
+    if (out_f32 != nullptr) out_f32[row * k_pad + c] = x;
+    if (out_bf16 != nullptr) out_bf16[row * k_pad + c] = __float2bfloat16_rn(x);
+  }
+}
+
+// ------------------------------------------------------------------ K2: query rows
+// One warp per query: [w_c * q_hat | w_f * u | 0-pad]; q_hat is either the
+// normalized raw embedding or a stored catalog row (liked set, global id).
+__global__ void __launch_bounds__(256)
+prep_queries_kernel(const float* __restrict__ q_emb, const int32_t* __restrict__ q_item, const float* __restrict__ q_cf,
+                    const float* __restrict__ w_c, const float* __restrict__ w_f, float w_c_all, float w_f_all,
+                    int n_queries, int dim, int cf_dim, int k_pad, int metric, const float* __restrict__ cat_f32,
+                    const __nv_bfloat16* __restrict__ cat_bf16, int64_t id_offset, int64_t n_items,
+                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int32_t* err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_queries) return;
+  const float wc = w_c != nullptr ? __ldg(w_c + row) : w_c_all;
+  const float wf = w_f != nullptr ? __ldg(w_f + row) : w_f_all;
+  int64_t src_item = -1;
+  if (q_item != nullptr) {
+    src_item = static_cast<int64_t>(__ldg(q_item + row)) - id_offset;
+    if (src_item < 0 || src_item >= n_items) {
+      if (lane == 0) atomicExch(err_flag, 1);
+      src_item = -2;
+    }
+  }
+  float den = 1.f;
+  if (q_emb != nullptr && src_item == -1 && metric == BB_METRIC_COSINE) {
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+      const float x = __ldg(q_emb + static_cast<int64_t>(row) * dim + c);
+      ss = fmaf(x, x, ss);
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    den = (nrm == 0.f) ? 1.f : nrm;
+  }
+  for (int c = lane; c < k_pad; c += 32) {
+    float x = 0.f;
+    if (c < dim) {
+      if (src_item >= 0) {
+        x = cat_f32 != nullptr ? __ldg(cat_f32 + src_item * k_pad + c) : __bfloat162float(cat_bf16[src_item * k_pad + c]);
+        x = __fmul_rn(wc, x);
+      } else if (q_emb != nullptr && src_item == -1) {
+        x = __fmul_rn(wc, __fdiv_rn(__ldg(q_emb + static_cast<int64_t>(row) * dim + c), den));
+      }
+    } else if (c < dim + cf_dim && q_cf != nullptr) {
+      x = __fmul_rn(wf, __ldg(q_cf + static_cast<int64_t>(row) * cf_dim + (c - dim)));
+    }
+    out_f32[static_cast<int64_t>(row) * k_pad + c] = x;
+    out_bf16[static_cast<int64_t>(row) * k_pad + c] = __float2bfloat16_rn(x);
+  }
+}
+
+__global__ void pack_meta_kernel(const int32_t* __restrict__ num_parts, const int16_t* __restrict__ year,
+                                 const int16_t* __restrict__ theme, int64_t n, int2* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t p = num_parts != nullptr ? num_parts[i] : 1;
+  const int32_t y = year != nullptr ? year[i] : 0;
+  const int32_t t = theme != nullptr ? theme[i] : -1;
+  out[i] = make_int2(p, (y & 0xffff) | (t << 16));
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ cat_f32, const __nv_bfloat16* __restrict__ cat_bf16,
+                                   int k_pad, int dim, int64_t id_offset, int64_t n_items,
+                                   const int32_t* __restrict__ ids, int n, float* __restrict__ out, int32_t* err_flag) {
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int64_t item = static_cast<int64_t>(ids[r]) - id_offset;
+  if (item < 0 || item >= n_items) {
+    if (lane == 0) atomicExch(err_flag, 1);
+    return;
+  }
+  for (int c = lane; c < dim; c += 32)
+    out[static_cast<int64_t>(r) * dim + c] =
+        cat_f32 != nullptr ? cat_f32[item * k_pad + c] : __bfloat162float(cat_bf16[item * k_pad + c]);
+}
+
+// ------------------------------------------------------------------ K3: constraint mask
+// grid.y = constraint; each warp produces 32-bit words of the bitmap (lane = item).
+// Algorithmic bytes: 8 B metadata read + 1/8 B written per item per constraint.
+__global__ void __launch_bounds__(256)
+mask_kernel(const ScanParams P, uint32_t* __restrict__ out_bitmaps, unsigned long long* __restrict__ out_counts) {
+  const int lane = threadIdx.x & 31;
+  const int c_idx = blockIdx.y;
+  const bb_constraint c = P.cons[c_idx];
+  const int64_t n_words = (P.n_items + 31) >> 5;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  unsigned long long count = 0;
+  for (int64_t w = warp0; w < n_words; w += n_warps) {
+    const int64_t item = (w << 5) + lane;
+    const bool ok = item < P.n_items && constraint_ok(P, c, item);
+    const unsigned bits = __ballot_sync(kFull, ok);
+    if (lane == 0) {
+      out_bitmaps[static_cast<int64_t>(c_idx) * n_words + w] = bits;
+      count += __popc(bits);
+    }
+  }
+  if (lane == 0 && count) atomicAdd(out_counts + c_idx, count);
+}
+
+// ------------------------------------------------------------------ running top-k' merger (one warp)
+// stage[0..127] = best so far (sorted descending after a flush), stage[128..255] = new keys.
+struct WarpMerger {
+  uint64_t* stage;
+  int n_new;
+  int lane;
+  __device__ void init(uint64_t* s, int l) {
+    stage = s; n_new = 0; lane = l;
+    for (int i = lane; i < kCap; i += 32) stage[i] = 0ull;
+    __syncwarp();
+  }
+  __device__ void flush() {
+    uint64_t v[kEpl];
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) v[i] = stage[(i << 5) | lane];
+    __syncwarp();
+    warp_sort_desc<kEpl>(v, lane);
+#pragma unroll
+    for (int i = 0; i < kEpl; ++i) stage[(i << 5) | lane] = (i < kEpl / 2) ? v[i] : 0ull;
+    n_new = 0;
+    __syncwarp();
+  }
+  // every lane offers one key (0 = nothing)
+  __device__ void offer(uint64_t key) {
+    const unsigned m = __ballot_sync(kFull, key != 0ull);
+    if (m == 0) return;
+    if (key != 0ull) stage[kCap / 2 + n_new + __popc(m & ((1u << lane) - 1u))] = key;
+    n_new += __popc(m);
+    __syncwarp();
+    if (n_new + 32 > kCap / 2) flush();
+  }
+};
+
+// ------------------------------------------------------------------ K4 + K6: merge, re-score, emit
+// One CTA (4 warps) per query.  Phase 1 (warp 0): gather every split's surviving
+// candidates that are still >= the final shared threshold and keep the best k_sel.
+// Phase 2 (all warps, optional): exact fp32 re-score of the survivors against the
+// fp32 operand copy (gather of k_sel rows of k_pad floats).  Phase 3: final sort, emit.
+__global__ void __launch_bounds__(128)
+merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restrict__ q_f32,
+                  const float* __restrict__ cat_f32, int as_l2, float* __restrict__ out_scores,
+                  int32_t* __restrict__ out_ids) {
+  __shared__ uint64_t stage[kCap];
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (warp == 0) {
+    WarpMerger mg;
+    mg.init(stage, lane);
+    const uint32_t thr = __ldcg(P.thr_g + q);
+    for (int s = 0; s < P.n_splits; ++s) {
+      const int64_t slot = static_cast<int64_t>(s) * P.b_pad + q;
+      const int cnt = __ldcg(P.cand_cnt + slot);
+      const uint64_t* buf = P.cand + slot * kCap;
+      for (int base = 0; base < cnt; base += 32) {
+        uint64_t key = (base + lane < cnt) ? __ldcg(buf + base + lane) : 0ull;
+        if (static_cast<uint32_t>(key >> 32) < thr) key = 0ull;
+        mg.offer(key);
+      }
+    }
+    mg.flush();
+  }
+  __syncthreads();
+
+  if (rescore) {
+    // exact fp32 dot of the query operand with each surviving catalog row
+    const float4* qv = reinterpret_cast<const float4*>(q_f32 + static_cast<int64_t>(q) * P.k_pad);
+    const int n4 = P.k_pad >> 2;
+    for (int c = warp; c < kMaxSel; c += 4) {
+      const uint64_t key = stage[c];
+      if (key == 0ull) continue;                       // warp-uniform
+      const int32_t gid = key_id(key);
+      const float4* ev = reinterpret_cast<const float4*>(cat_f32 + (static_cast<int64_t>(gid) - P.id_offset) * P.k_pad);
+      float acc = 0.f;
+      for (int i = lane; i < n4; i += 32) {
+        const float4 a = __ldg(qv + i), b = __ldg(ev + i);
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) stage[c] = make_key(acc, static_cast<uint32_t>(gid));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t v[kEpl / 2];
+#pragma unroll
+      for (int i = 0; i < kEpl / 2; ++i) v[i] = stage[(i << 5) | lane];
+      __syncwarp();
+      warp_sort_desc<kEpl / 2>(v, lane);
+#pragma unroll
+      for (int i = 0; i < kEpl / 2; ++i) stage[(i << 5) | lane] = v[i];
+    }
+    __syncthreads();
+  }
+
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const uint64_t key = stage[i];
+    float s = -INFINITY;
+    int32_t id = -1;
+    if (key != 0ull) {
+      s = key_score(key);
+      id = key_id(key);
+      if (as_l2) s = 2.f - 2.f * s;
+    } else if (as_l2) {
+      s = INFINITY;
+    }
+    out_scores[static_cast<int64_t>(q) * k + i] = s;
+    out_ids[static_cast<int64_t>(q) * k + i] = id;
+  }
+}
+
+// ------------------------------------------------------------------ cross-shard merge of (score, id) lists
+__global__ void __launch_bounds__(128)
+merge_lists_kernel(int n_queries, int n_lists, int len, const float* __restrict__ scores,
+                   const int32_t* __restrict__ ids, int k, float* __restrict__ out_scores,
+                   int32_t* __restrict__ out_ids) {
+  __shared__ uint64_t stage_all[4][kCap];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * 4 + warp;
+  if (q >= n_queries) return;
+  uint64_t* stage = stage_all[warp];
+  WarpMerger mg;
+  mg.init(stage, lane);
+  for (int l = 0; l < n_lists; ++l) {
+    const int64_t base = (static_cast<int64_t>(l) * n_queries + q) * len;
+    for (int i = 0; i < len; i += 32) {
+      uint64_t key = 0ull;
+      if (i + lane < len) {
+        const int32_t id = __ldg(ids + base + i + lane);
+        if (id >= 0) key = make_key(__ldg(scores + base + i + lane), static_cast<uint32_t>(id));
+      }
+      mg.offer(key);
+    }
+  }
+  mg.flush();
+  for (int i = lane; i < k; i += 32) {
+    const uint64_t key = stage[i];
+    out_scores[static_cast<int64_t>(q) * k + i] = key ? key_score(key) : -INFINITY;
+    out_ids[static_cast<int64_t>(q) * k + i] = key ? key_id(key) : -1;
+  }
+}
+
+// ------------------------------------------------------------------ K5: reference-semantics hybrid combine
+// recommendation_system.py:789-843 -- union of the two lists, missing side = 0,
+// python-float (fp64) blend without FMA contraction, rank by (-score, +id).
+constexpr int kHybMax = 512;
+__global__ void __launch_bounds__(128)
+hybrid_combine_kernel(int len_c, const int32_t* __restrict__ c_ids, const float* __restrict__ c_scores, int len_f,
+                      const int32_t* __restrict__ f_ids, const float* __restrict__ f_scores,
+                      const double* __restrict__ weights, int weights_per_row, int k, double* __restrict__ out_scores,
+                      int32_t* __restrict__ out_ids) {
+  __shared__ int32_t u_id[kHybMax];
+  __shared__ double u_sc[kHybMax];
+  __shared__ int n_union;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const double wc = weights[weights_per_row ? 2 * row : 0], wf = weights[weights_per_row ? 2 * row + 1 : 1];
+  const int32_t* ci = c_ids + static_cast<int64_t>(row) * len_c;
+  const float* cs = c_scores + static_cast<int64_t>(row) * len_c;
+  const int32_t* fi = f_ids + static_cast<int64_t>(row) * len_f;
+  const float* fs = f_scores + static_cast<int64_t>(row) * len_f;
+  if (tid == 0) n_union = 0;
+  __syncthreads();
+  for (int i = tid; i < len_c; i += blockDim.x) {
+    const int32_t id = ci[i];
+    if (id < 0) continue;
+    double f = 0.0;
+    for (int j = 0; j < len_f; ++j)
+      if (fi[j] == id) f = static_cast<double>(fs[j]);
+    const int slot = atomicAdd(&n_union, 1);
+    u_id[slot] = id;
+    u_sc[slot] = __dadd_rn(__dmul_rn(wc, static_cast<double>(cs[i])), __dmul_rn(wf, f));
+  }
+  for (int j = tid; j < len_f; j += blockDim.x) {
+    const int32_t id = fi[j];
+    if (id < 0) continue;
+    bool in_c = false;
+    for (int i = 0; i < len_c; ++i) in_c |= (ci[i] == id);
+    if (in_c) continue;
+    const int slot = atomicAdd(&n_union, 1);
+    u_id[slot] = id;
+    u_sc[slot] = __dadd_rn(__dmul_rn(wc, 0.0), __dmul_rn(wf, static_cast<double>(fs[j])));
+  }
+  __syncthreads();
+  const int n = n_union;
+  for (int i = tid; i < k; i += blockDim.x) {
+    out_scores[static_cast<int64_t>(row) * k + i] = -INFINITY;
+    out_ids[static_cast<int64_t>(row) * k + i] = -1;
+  }
+  __syncthreads();
+  for (int e = tid; e < n; e += blockDim.x) {
+    const double s = u_sc[e];
+    const int32_t id = u_id[e];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) {
+      const double so = u_sc[o];
+      rank += (so > s) || (so == s && u_id[o] < id);
+    }
+    if (rank < k) {
+      out_scores[static_cast<int64_t>(row) * k + rank] = s;
+      out_ids[static_cast<int64_t>(row) * k + rank] = id;
+    }
+  }
+}
+
+inline int blocks_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
+
+}  // namespace
+
+cudaError_t launch_prep_catalog(const float* emb, const float* cf, int64_t n_rows, int dim, int cf_dim, int k_pad,
+                                int metric, float* out_f32, void* out_bf16, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  prep_catalog_kernel<<<blocks_for(n_rows, 8), 256, 0, stream>>>(emb, cf, n_rows, dim, cf_dim, k_pad, metric, out_f32,
+                                                                static_cast<__nv_bfloat16*>(out_bf16));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const float* q_cf, const float* w_c,
+                                const float* w_f, float w_c_all, float w_f_all, int n_queries, int dim, int cf_dim,
+                                int k_pad, int metric, const float* cat_f32, const void* cat_bf16, int64_t id_offset,
+                                int64_t n_items, float* out_f32, void* out_bf16, int32_t* err_flag,
+                                cudaStream_t stream) {
+  prep_queries_kernel<<<blocks_for(n_queries, 8), 256, 0, stream>>>(
+      q_emb, q_item, q_cf, w_c, w_f, w_c_all, w_f_all, n_queries, dim, cf_dim, k_pad, metric, cat_f32,
+      static_cast<const __nv_bfloat16*>(cat_bf16), id_offset, n_items, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
+      err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_meta(const int32_t* num_parts, const int16_t* year, const int16_t* theme, int64_t n_rows,
+                             int2* out, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  pack_meta_kernel<<<blocks_for(n_rows, 256), 256, 0, stream>>>(num_parts, year, theme, n_rows, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  fill_u32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* cat_f32, const void* cat_bf16, int k_pad, int dim, int64_t id_offset,
+                               int64_t n_items, const int32_t* ids, int n, float* out, int32_t* err_flag,
+                               cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  gather_rows_kernel<<<blocks_for(n, 8), 256, 0, stream>>>(cat_f32, static_cast<const __nv_bfloat16*>(cat_bf16), k_pad,
+                                                          dim, id_offset, n_items, ids, n, out, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bitmaps, unsigned long long* out_counts,
+                        cudaStream_t stream) {
+  const int64_t n_words = (P.n_items + 31) >> 5;
+  int bx = static_cast<int>((n_words + 7) / 8);
+  if (bx > 148 * 8) bx = 148 * 8;       // grid-stride: 8 resident CTAs per SM
+  if (bx < 1) bx = 1;
+  mask_kernel<<<dim3(bx, n_constraints), 256, 0, stream>>>(P, out_bitmaps, out_counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_emit(const ScanParams& P, int k, bool rescore, const float* q_f32, const float* cat_f32,
+                              bool as_l2, float* out_scores, int32_t* out_ids, cudaStream_t stream) {
+  merge_emit_kernel<<<P.n_queries, 128, 0, stream>>>(P, k, rescore ? 1 : 0, q_f32, cat_f32, as_l2 ? 1 : 0, out_scores,
+                                                     out_ids);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_lists(int n_queries, int n_lists, int len, const float* scores, const int32_t* ids, int k,
+                               float* out_scores, int32_t* out_ids, cudaStream_t stream) {
+  merge_lists_kernel<<<blocks_for(n_queries, 4), 128, 0, stream>>>(n_queries, n_lists, len, scores, ids, k, out_scores,
+                                                                  out_ids);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hybrid_combine(int n_rows, int len_c, const int32_t* c_ids, const float* c_scores, int len_f,
+                                  const int32_t* f_ids, const float* f_scores, const double* weights,
+                                  int weights_per_row, int k, double* out_scores, int32_t* out_ids,
+                                  cudaStream_t stream) {
+  hybrid_combine_kernel<<<n_rows, 128, 0, stream>>>(len_c, c_ids, c_scores, len_f, f_ids, f_scores, weights,
+                                                    weights_per_row, k, out_scores, out_ids);
+  return cudaGetLastError();
+}
+
+}  // namespace bb

@@ -1,0 +1,434 @@
+// K1 -- tcgen05 bf16 scan: TMA-fed UMMA (fp32 accumulate in TMEM) with the fused
+// hybrid blend (folded into the operands) + hard-constraint mask + running-threshold
+// top-k epilogue.  Score tiles never leave the SM: only candidates that beat the
+// per-query threshold are written (8 B each) to L2-resident candidate buffers.
+//
+// Decomposition (query-stationary):
+//   * a CTA group = 1 CTA (cta_group::1) or a 2-CTA cluster on one TPC (cta_group::2).
+//   * the group owns 128*CG query rows; their whole bf16 operand (<= 7 k-blocks of
+//     64 columns, 16 KB each, 128B-swizzled, K-major) stays RESIDENT in shared memory
+//     for a unit, so L2->SM traffic is the catalog stream only.
+//   * the catalog streams through a TMA ring of [256/CG rows x 64 cols] stages; one
+//     UMMA tile is 128*CG queries x 256 items; two 256-column TMEM accumulators are
+//     double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * work unit = (query block, catalog split); units are dealt round-robin to groups.
+//
+// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA),
+// 2 = TMEM allocator, 3 = idle, 4..7 = epilogue (TMEM lane quarter = warp % 4,
+// one thread per query row).
+//
+// Roofline: tensor core.  2*128*256*k_pad flop per CTA tile; catalog bytes
+// 256*k_pad*2 per group tile.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "bb_common.cuh"
+#include "bb_kernels.h"
+
+namespace bb {
+namespace {
+
+constexpr int kBlockK = 64;                 // bf16 columns per k-block (= one 128 B swizzle row)
+constexpr int kAkbBytes = 128 * 128;        // resident query k-block: 128 rows x 128 B
+constexpr int kUmmaK = 16;
+constexpr int kAccCols = 256;               // fp32 accumulator columns per tile
+constexpr int kTmemCols = 512;              // two accumulators
+constexpr int kThreads = 256;
+constexpr int kStageBytesEpi = 4 * 32 * 32 * 4;   // per-warp [32 cols][32 lanes] score staging
+constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
+
+template <int CG> struct Cfg {
+  static constexpr int kBRows = kTcTile / CG;            // catalog rows this CTA loads per stage
+  static constexpr int kBStageBytes = kBRows * 128;
+  static constexpr int kStages = (CG == 2) ? 5 : 3;
+  static constexpr int kSmemBytes = kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kStageBytesEpi + 512 + 1024;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) {
+      if (err_flag != nullptr) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t bar, uint32_t dst, int32_t c0, int32_t c1) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+  } else {
+    // bar is the LEADER CTA's barrier in the shared::cluster window: both CTAs' bytes
+    // complete one transaction barrier that the single MMA issuer waits on.
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG> __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// tcgen05.commit: arrives on `bar` (same smem offset in every CTA of the group) once all
+// previously issued MMAs of this thread have completed.
+template <int CG> __device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B,
+// 8-row groups 1024 B apart).  Field layout: start[0,14) | LBO[16,30) | SBO[32,46) |
+// version[46,48)=1 | layout[61,64)=2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
+               const ScanParams P, const int n_groups) {
+  using C = Cfg<CG>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + kTcMaxKBlocks * kAkbBytes;
+  float* smem_stage = reinterpret_cast<float*>(smem_b + C::kStages * C::kBStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem_stage) + kStageBytesEpi);
+  uint64_t* bar_full = bars;                      // [kStages]  TMA -> MMA     (leader's are used)
+  uint64_t* bar_empty = bars + C::kStages;        // [kStages]  MMA -> TMA     (per CTA)
+  uint64_t* bar_a_full = bars + 2 * C::kStages;   //            TMA -> MMA     (leader)
+  uint64_t* bar_a_empty = bar_a_full + 1;         //            MMA -> TMA     (per CTA)
+  uint64_t* bar_acc_full = bar_a_full + 2;        // [2]        MMA -> epilogue (per CTA)
+  uint64_t* bar_acc_empty = bar_a_full + 4;       // [2]        epilogue -> MMA (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a_full + 6);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int group = blockIdx.x / CG;
+  const int n_kb = P.k_pad / kBlockK;
+  const int n_units = P.n_qblocks * P.n_splits;
+  int32_t* err = P.err_flag;
+
+  if (tid == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(bar_full + s), 1);
+      mbar_init(smem_u32(bar_empty + s), 1);
+    }
+    mbar_init(smem_u32(bar_a_full), 1);
+    mbar_init(smem_u32(bar_a_empty), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(bar_acc_full + a), 1);
+      mbar_init(smem_u32(bar_acc_empty + a), CG * 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_e);
+  }
+  if (warp == 2) tmem_alloc<CG>(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      const uint32_t a_full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_a_full), 0) : smem_u32(bar_a_full);
+      for (int u = group; u < n_units; u += n_groups) {
+        const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
+        int t0, t1;
+        split_tile_range(P, split, t0, t1);
+        const int row0 = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta;
+        // resident query operand: wait until the previous unit's MMAs stopped reading it
+        mbar_wait(smem_u32(bar_a_empty), a_phase ^ 1, err, 101);
+        a_phase ^= 1;
+        if (leader) mbar_arrive_expect_tx(smem_u32(bar_a_full), static_cast<uint32_t>(CG * n_kb * kAkbBytes));
+        for (int kb = 0; kb < n_kb; ++kb)
+          tma_load_2d<CG>(&tmap_q, a_full_leader, smem_u32(smem_a + kb * kAkbBytes), kb * kBlockK, row0);
+        for (int t = t0; t < t1; ++t) {
+          const int item0 = t * kTcTile + static_cast<int>(cta_rank) * C::kBRows;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(smem_u32(bar_empty + stage), phase ^ 1, err, 102);
+            const uint32_t full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_full + stage), 0) : smem_u32(bar_full + stage);
+            if (leader) mbar_arrive_expect_tx(smem_u32(bar_full + stage), static_cast<uint32_t>(CG * C::kBStageBytes));
+            tma_load_2d<CG>(&tmap_e, full_leader, smem_u32(smem_b + stage * C::kBStageBytes), kb * kBlockK, item0);
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA) ==============================
+    if (leader) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
+      constexpr uint32_t idesc = make_idesc(128 * CG, kTcTile);
+      for (int u = group; u < n_units; u += n_groups) {
+        const int split = u / P.n_qblocks;
+        int t0, t1;
+        split_tile_range(P, split, t0, t1);
+        mbar_wait(smem_u32(bar_a_full), a_phase, err, 103);
+        a_phase ^= 1;
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1, err, 104);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(smem_u32(bar_full + stage), phase, err, 105);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + kb * kAkbBytes));
+              const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * C::kBStageBytes));
+#pragma unroll
+              for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
+                umma_bf16<CG>(d_tmem, a_desc + static_cast<uint64_t>(ks * 2), b_desc + static_cast<uint64_t>(ks * 2), idesc,
+                              static_cast<uint32_t>((kb | ks) != 0));
+              }
+              umma_commit<CG>(smem_u32(bar_empty + stage));      // stage reusable once these MMAs retire
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+          if (lane == 0) umma_commit<CG>(smem_u32(bar_acc_full + acc));   // accumulator ready
+          __syncwarp();
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        if (lane == 0) umma_commit<CG>(smem_u32(bar_a_empty));            // query operand no longer read
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue: mask + running-threshold top-k ==============================
+    const int ew = warp & 3;                       // TMEM lane quarter this warp may read
+    float* stage_w = smem_stage + ew * 1024;
+    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t acc_empty_leader_base = (CG == 2) ? mapa_u32(smem_u32(bar_acc_empty), 0) : smem_u32(bar_acc_empty);
+    for (int u = group; u < n_units; u += n_groups) {
+      const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
+      int t0, t1;
+      split_tile_range(P, split, t0, t1);
+      const int q = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta + ew * 32 + lane;
+      const bool q_valid = q < P.n_queries;
+      RowState st;
+      st.thr = q_valid ? -INFINITY : INFINITY;
+      st.cnt = 0;
+      st.buf = P.cand + (static_cast<int64_t>(split) * P.b_pad + q) * kCap;
+      for (int t = t0; t < t1; ++t) {
+        if (q_valid && P.dump == nullptr) st.thr = fmaxf(st.thr, ord2f(__ldcg(P.thr_g + q)));
+        mbar_wait(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols;
+        const int64_t item0 = static_cast<int64_t>(t) * kTcTile;
+#pragma unroll 1
+        for (int chunk = 0; chunk < kAccCols / 32; ++chunk) {
+          uint32_t r[32];
+          tmem_ld32(taddr + chunk * 32, r);
+          tmem_ld_wait();
+          if (P.dump != nullptr) {
+            if (q_valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int64_t item = item0 + chunk * 32 + j;
+                if (item < P.n_items) P.dump[static_cast<int64_t>(q) * P.n_items + item] = __uint_as_float(r[j]);
+              }
+            }
+            continue;
+          }
+          float m = __uint_as_float(r[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+          if (__any_sync(kFull, m >= st.thr)) {
+            unsigned pm = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = __uint_as_float(r[j]);
+              stage_w[j * 32 + lane] = s;
+              pm |= (s >= st.thr) ? (1u << j) : 0u;
+            }
+            while (__any_sync(kFull, pm != 0u)) {
+              if (pm != 0u) {
+                const int j = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const float s = stage_w[j * 32 + lane];
+                const int64_t item = item0 + chunk * 32 + j;
+                if (item_ok(P, q, item)) row_append(P, st, s, item);
+              }
+            }
+            warp_compact_if_needed(P, st, q, lane);
+          }
+        }
+        // accumulator drained: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(acc_empty_leader_base + acc * 8);
+          else mbar_arrive_local(acc_empty_leader_base + acc * 8);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (P.dump == nullptr) {
+        P.cand_cnt[static_cast<int64_t>(split) * P.b_pad + q] = st.cnt;
+        if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
+      }
+    }
+  }
+
+  // ============================== teardown ==============================
+  __syncwarp();
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, kTmemCols);
+}
+
+}  // namespace
+
+cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* tmap_e, int cta_group, int n_groups,
+                           cudaStream_t stream) {
+  const CUtensorMap* tq = static_cast<const CUtensorMap*>(tmap_q);
+  const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e);
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = stream;
+  cudaError_t e;
+  if (cta_group == 2) {
+    e = cudaFuncSetAttribute(scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cfg.gridDim = dim3(n_groups * 2);
+    cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, scan_tc_kernel<2>, *tq, *te, P, n_groups);
+  }
+  e = cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  cfg.gridDim = dim3(n_groups);
+  cfg.dynamicSmemBytes = Cfg<1>::kSmemBytes;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
+  return cudaLaunchKernelEx(&cfg, scan_tc_kernel<1>, *tq, *te, P, n_groups);
+}
+
+}  // namespace bb

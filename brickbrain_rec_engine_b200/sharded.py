@@ -1,0 +1,58 @@
+"""Row-sharded catalog across the GPUs of one node.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink / NVSwitch).  Catalog
+rows, metadata and item factors are partitioned contiguously; queries and their
+constraint descriptors are replicated.  Each rank runs the fused scan over its
+shard and emits B x k (score, GLOBAL id) candidates; the only data-path
+collective is one all-gather of those candidates (B*k*8 bytes per rank), followed
+by a k-way merge kernel on every rank.  Ties stay (-score, +id) because ids are global.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range [begin, end) of ``rank``; remainders go to the low ranks."""
+    base, rem = divmod(n_items, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class ShardedSearch:
+    """Couples a per-rank engine (anything with ``search`` and ``merge_topk``) with the
+    candidate all-gather.  ``engine.id_offset`` must equal this rank's ``shard_bounds`` begin."""
+
+    def __init__(self, engine, group=None):
+        if dist is None or not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialized (one process per GPU)")
+        self.engine = engine
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def search(self, k: int, **kwargs):
+        """Same keyword arguments as ``ScoringEngine.search``; returns the GLOBAL top-k on every rank."""
+        scores, ids = self.engine.search(k, **kwargs)
+        if self.world_size == 1:
+            return scores, ids
+        as_torch = torch.is_tensor(scores)
+        s_t = scores if as_torch else torch.from_numpy(np.ascontiguousarray(scores))
+        i_t = ids if as_torch else torch.from_numpy(np.ascontiguousarray(ids))
+        b = s_t.shape[0]
+        all_s = torch.empty((self.world_size, b, k), dtype=s_t.dtype, device=s_t.device)
+        all_i = torch.empty((self.world_size, b, k), dtype=i_t.dtype, device=i_t.device)
+        dist.all_gather_into_tensor(all_s.view(-1), s_t.reshape(-1).contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_i.view(-1), i_t.reshape(-1).contiguous(), group=self.group)
+        if as_torch:
+            return self.engine.merge_topk(all_s, all_i, k)
+        return self.engine.merge_topk(all_s.numpy(), all_i.numpy(), k)
