@@ -53,7 +53,7 @@ struct DevBuf {
 
 struct Workspace {
   std::mutex mu;
-  DevBuf q_f32, q_bf16, cand, cand_cnt, thr_g, out_scores, out_ids, misc, stage, dump;
+  DevBuf q_f32, q_bf16, cand, cand_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid;
   alignas(64) CUtensorMap tmap_q;
   const void* tmap_q_ptr = nullptr;
   int tmap_q_rows = 0;
@@ -219,7 +219,7 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   if (splits > p.n_tiles) splits = p.n_tiles;
   if (splits < 1) splits = 1;
   // bound candidate memory (2 KB per (split, row)) to 2 GiB
-  const long long max_splits = (2ll << 30) / (static_cast<long long>(p.b_pad) * kCap * 8);
+  const long long max_splits = (2ll << 30) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? 2 : 1));
   if (splits > max_splits) splits = max_splits > 0 ? max_splits : 1;
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
@@ -328,12 +328,17 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.n_qblocks = plan.n_qblocks;
   P.n_splits = plan.n_splits;
   P.n_tiles = plan.n_tiles;
+  P.n_sub = tc ? 2 : 1;
   P.tile_items = plan.tile_items;
   P.dump = dump;
   P.stat_candidates = h->stat_dev;
   P.err_flag = h->err_dev;
+  {
+    const char* dbg = getenv("BB_DEBUG_FLAGS");
+    P.debug_flags = dbg != nullptr ? atoi(dbg) : 0;
+  }
   if (dump == nullptr) {
-    const size_t slots = static_cast<size_t>(plan.n_splits) * plan.b_pad;
+    const size_t slots = static_cast<size_t>(plan.n_splits) * P.n_sub * plan.b_pad;
     BB_CUDA(h, w->cand.ensure(slots * kCap * sizeof(uint64_t)));
     BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
     BB_CUDA(h, w->thr_g.ensure(static_cast<size_t>(plan.b_pad) * sizeof(uint32_t)));
@@ -343,6 +348,20 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     BB_CUDA(h, launch_fill_u32(P.thr_g, kOrdNegInf, plan.b_pad, stream));
     BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, sizeof(unsigned long long), stream));
     h->launches++;
+  }
+
+  // ---- one constraint shared by the whole batch: evaluate it once per item with the mask kernel (K3); the scan
+  //      epilogue then masks a 32-item chunk with a single word of the bitmap
+  if (tc && dump == nullptr && q->n_constraints == 1 && B > 1) {
+    const int64_t words = (h->cfg.n_items + 31) / 32;
+    BB_CUDA(h, w->shared_valid.ensure(static_cast<size_t>(words) * sizeof(uint32_t) + 64));
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(w->shared_valid.p) +
+                                                                     static_cast<size_t>(words) * sizeof(uint32_t));
+    cnt = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(cnt) + 7) & ~static_cast<uintptr_t>(7));
+    BB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), stream));
+    BB_CUDA(h, launch_mask(P, 1, static_cast<uint32_t*>(w->shared_valid.p), cnt, stream));
+    h->launches++;
+    P.shared_valid = static_cast<const uint32_t*>(w->shared_valid.p);
   }
 
   // ---- scan
@@ -479,7 +498,7 @@ void bb_destroy(bb_handle* h) {
   for (auto& kv : h->ws) {
     Workspace* w = kv.second;
     for (DevBuf* b : {&w->q_f32, &w->q_bf16, &w->cand, &w->cand_cnt, &w->thr_g, &w->out_scores, &w->out_ids, &w->misc,
-                      &w->stage, &w->dump})
+                      &w->stage, &w->dump, &w->shared_valid})
       b->release();
     if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
     delete w;

@@ -202,7 +202,7 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     WarpMerger mg;
     mg.init(stage, lane);
     const uint32_t thr = __ldcg(P.thr_g + q);
-    for (int s = 0; s < P.n_splits; ++s) {
+    for (int s = 0; s < P.n_splits * P.n_sub; ++s) {
       const int64_t slot = static_cast<int64_t>(s) * P.b_pad + q;
       const int cnt = __ldcg(P.cand_cnt + slot);
       const uint64_t* buf = P.cand + slot * kCap;

@@ -99,7 +99,9 @@ struct ScanParams {
   int64_t allow_words;
   const int64_t* excl_off;
   const int32_t* excl_ids;
-  // candidate buffers: cand[(split * b_pad + row) * kCap + i], cnt[split * b_pad + row]
+  const uint32_t* shared_valid;   // validity bitmap of the single shared constraint (built by the mask kernel) or nullptr
+  // candidate buffers: slot = (split * n_sub + sub) * b_pad + row; cand[slot * kCap + i], cnt[slot]
+  int32_t n_sub;          // buffers per (split, row): the tcgen05 epilogue uses one per column half
   uint64_t* cand;
   int32_t* cand_cnt;
   uint32_t* thr_g;        // per-row shared running threshold (ordered bits), max over splits
@@ -112,6 +114,7 @@ struct ScanParams {
   float* dump;            // dense [b x n_items] score dump (bb_debug_scores) or nullptr
   unsigned long long* stat_candidates;
   int32_t* err_flag;      // set by watchdogs before trapping
+  int32_t debug_flags;    // perf triage (env BB_DEBUG_FLAGS): 1 = epilogue never inserts, 2 = epilogue skips TMEM loads
 };
 
 __device__ __forceinline__ void split_tile_range(const ScanParams& P, int split, int& t0, int& t1) {

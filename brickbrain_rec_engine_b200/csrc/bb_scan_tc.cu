@@ -14,8 +14,8 @@
 //   * work unit = (query block, catalog split); units are dealt round-robin to groups.
 //
 // Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA),
-// 2 = TMEM allocator, 3 = idle, 4..7 = epilogue (TMEM lane quarter = warp % 4,
-// one thread per query row).
+// 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (TMEM lane quarter = warp % 4; the two
+// warps of a quarter split the tile's 256 columns; one thread per (query row, column half)).
 //
 // Roofline: tensor core.  2*128*256*k_pad flop per CTA tile; catalog bytes
 // 256*k_pad*2 per group tile.
@@ -33,15 +33,19 @@ constexpr int kAkbBytes = 128 * 128;        // resident query k-block: 128 rows 
 constexpr int kUmmaK = 16;
 constexpr int kAccCols = 256;               // fp32 accumulator columns per tile
 constexpr int kTmemCols = 512;              // two accumulators
-constexpr int kThreads = 256;
-constexpr int kStageBytesEpi = 4 * 32 * 32 * 4;   // per-warp [32 cols][32 lanes] score staging
+constexpr int kEpiWarps = 8;                // two warps per TMEM lane quarter, each scans half of the tile's columns
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr int kChunksPerWarp = (kAccCols / 32) / (kEpiWarps / 4);
+constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata of the 32 columns of a chunk
+constexpr int kThemeBytes = 32 * 128 * 4;         // per-row allowed-theme bitmaps, word-major [32 words][128 rows]
 constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
 
 template <int CG> struct Cfg {
   static constexpr int kBRows = kTcTile / CG;            // catalog rows this CTA loads per stage
   static constexpr int kBStageBytes = kBRows * 128;
-  static constexpr int kStages = (CG == 2) ? 5 : 3;
-  static constexpr int kSmemBytes = kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kStageBytesEpi + 512 + 1024;
+  static constexpr int kStages = (CG == 2) ? 5 : 2;
+  static constexpr int kSmemBytes =
+      kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kColMetaBytes + kThemeBytes + 512 + 1024;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -203,8 +207,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + kTcMaxKBlocks * kAkbBytes;
-  float* smem_stage = reinterpret_cast<float*>(smem_b + C::kStages * C::kBStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem_stage) + kStageBytesEpi);
+  uint4* smem_colmeta = reinterpret_cast<uint4*>(smem_b + C::kStages * C::kBStageBytes);
+  uint32_t* smem_theme = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(smem_colmeta) + kColMetaBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem_theme) + kThemeBytes);
   uint64_t* bar_full = bars;                      // [kStages]  TMA -> MMA     (leader's are used)
   uint64_t* bar_empty = bars + C::kStages;        // [kStages]  MMA -> TMA     (per CTA)
   uint64_t* bar_a_full = bars + 2 * C::kStages;   //            TMA -> MMA     (leader)
@@ -230,7 +235,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     mbar_init(smem_u32(bar_a_empty), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(bar_acc_full + a), 1);
-      mbar_init(smem_u32(bar_acc_empty + a), CG * 4);
+      mbar_init(smem_u32(bar_acc_empty + a), CG * kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -316,28 +321,53 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
   } else if (warp >= 4) {
     // ============================== epilogue: mask + running-threshold top-k ==============================
-    const int ew = warp & 3;                       // TMEM lane quarter this warp may read
-    float* stage_w = smem_stage + ew * 1024;
+    const int ew = warp & 3;                        // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;               // which column half of every tile this warp scans
+    const int row_in_cta = ew * 32 + lane;
+    uint4* colmeta_w = smem_colmeta + (warp - 4) * 32;
+    uint32_t* theme_row = smem_theme + row_in_cta;  // this row's allowed-theme words at [w * 128]
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t acc_empty_leader_base = (CG == 2) ? mapa_u32(smem_u32(bar_acc_empty), 0) : smem_u32(bar_acc_empty);
+    const bool use_cons = P.cons != nullptr && P.shared_valid == nullptr;
     for (int u = group; u < n_units; u += n_groups) {
       const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
       int t0, t1;
       split_tile_range(P, split, t0, t1);
-      const int q = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta + ew * 32 + lane;
+      const int q = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta + row_in_cta;
       const bool q_valid = q < P.n_queries;
+      // the row's cheap predicates (integer ranges + allowed-theme bitmap) live in registers / smem so that a
+      // score that beats the threshold is masked without touching global memory
+      int pmin = INT32_MIN, ymin = -32768;
+      unsigned prange = 0xffffffffu, yrange = 0xffffu;
+      bool has_theme = false, dead = !q_valid;
+      if (q_valid && P.cons != nullptr) {
+        const bb_constraint c = P.cons[static_cast<int64_t>(q) * P.cons_stride];
+        if ((c.flags & BB_C_ALWAYS_FALSE) || c.parts_max < c.parts_min || c.year_max < c.year_min) dead = true;
+        pmin = c.parts_min;
+        prange = static_cast<unsigned>(c.parts_max) - static_cast<unsigned>(c.parts_min);
+        ymin = c.year_min;
+        yrange = static_cast<unsigned>(static_cast<int>(c.year_max) - static_cast<int>(c.year_min));
+        if (use_cons && c.theme_set >= 0 && P.theme_words <= 32) {
+          has_theme = true;
+          const uint32_t* src = P.theme_sets + static_cast<int64_t>(c.theme_set) * P.theme_words;
+          for (int w = 0; w < 32; ++w) theme_row[w * 128] = (w < P.theme_words) ? __ldg(src + w) : 0u;   // both halves write the same words
+        }
+      }
+      const bool any_theme = __any_sync(kFull, has_theme);
       RowState st;
-      st.thr = q_valid ? -INFINITY : INFINITY;
+      st.thr = dead ? INFINITY : -INFINITY;
       st.cnt = 0;
-      st.buf = P.cand + (static_cast<int64_t>(split) * P.b_pad + q) * kCap;
+      const int64_t slot = (static_cast<int64_t>(split) * P.n_sub + half) * P.b_pad + q;
+      st.buf = P.cand + slot * kCap;
       for (int t = t0; t < t1; ++t) {
-        if (q_valid && P.dump == nullptr) st.thr = fmaxf(st.thr, ord2f(__ldcg(P.thr_g + q)));
+        if (!dead && P.dump == nullptr) st.thr = fmaxf(st.thr, ord2f(__ldcg(P.thr_g + q)));
         mbar_wait(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols;
         const int64_t item0 = static_cast<int64_t>(t) * kTcTile;
 #pragma unroll 1
-        for (int chunk = 0; chunk < kAccCols / 32; ++chunk) {
+        for (int chunk = half * kChunksPerWarp; chunk < (half + 1) * kChunksPerWarp; ++chunk) {
+          if (P.debug_flags & 2) break;
           uint32_t r[32];
           tmem_ld32(taddr + chunk * 32, r);
           tmem_ld_wait();
@@ -354,24 +384,67 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           float m = __uint_as_float(r[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-          if (__any_sync(kFull, m >= st.thr)) {
-            unsigned pm = 0;
+          if (__any_sync(kFull, m >= st.thr) && !(P.debug_flags & 1)) {
+            // ---- slow path, entered only when some row of this warp has a score >= its threshold
+            unsigned pm = 0;                                   // per row: columns whose score passes
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(r[j]);
-              stage_w[j * 32 + lane] = s;
-              pm |= (s >= st.thr) ? (1u << j) : 0u;
-            }
-            while (__any_sync(kFull, pm != 0u)) {
-              if (pm != 0u) {
-                const int j = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const float s = stage_w[j * 32 + lane];
-                const int64_t item = item0 + chunk * 32 + j;
-                if (item_ok(P, q, item)) row_append(P, st, s, item);
+            for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= st.thr) ? (1u << j) : 0u;
+            const int64_t col_item = item0 + chunk * 32 + lane;   // this lane also "owns" one column's metadata
+            pm &= ~__ballot_sync(kFull, col_item >= P.n_items);
+            if (P.shared_valid != nullptr) {
+              // one constraint shared by the whole batch: its validity bitmap was built by the mask kernel
+              pm &= __ldg(P.shared_valid + ((item0 + chunk * 32) >> 5));
+            } else if (use_cons) {
+              unsigned cols = __reduce_or_sync(kFull, pm);     // columns with at least one passing row (uniform)
+              if (cols != 0u) {
+                // column owners unpack their item's metadata once; rows then read it as a shared-memory broadcast
+                int2 mt = make_int2(0, 0);
+                if (col_item < P.n_items) mt = __ldg(P.meta + col_item);
+                const int c_theme = mt.y >> 16;
+                uint4 cm;
+                cm.x = static_cast<unsigned>(mt.x);                                            // num_parts
+                cm.y = static_cast<unsigned>(static_cast<int>(static_cast<int16_t>(mt.y & 0xffff)));   // year
+                cm.z = static_cast<unsigned>(c_theme >= 0 ? min(c_theme >> 5, 31) : 0) * 128u;  // theme word offset
+                cm.w = (c_theme >= 0 && c_theme < 1024) ? (1u << (c_theme & 31)) : 0u;          // theme bit (0 = NULL)
+                __syncwarp();
+                colmeta_w[lane] = cm;
+                __syncwarp();
+                unsigned vm = 0;
+                while (cols != 0u) {
+                  const int j = __ffs(cols) - 1;
+                  cols &= cols - 1;
+                  const uint4 c4 = colmeta_w[j];
+                  bool ok = (c4.x - static_cast<unsigned>(pmin) <= prange) &&
+                            (c4.y - static_cast<unsigned>(ymin) <= yrange);
+                  if (any_theme) ok = ok && (!has_theme || (theme_row[c4.z] & c4.w) != 0u);
+                  vm |= ok ? (1u << j) : 0u;
+                }
+                pm &= vm;
               }
             }
-            warp_compact_if_needed(P, st, q, lane);
+            if (__any_sync(kFull, pm != 0u)) {
+              // ---- rare: a masked-in candidate exists
+              while (__any_sync(kFull, pm != 0u)) {
+                if (pm != 0u) {
+                  const int j = __ffs(pm) - 1;
+                  pm &= pm - 1;
+                  // r[j] with a run-time j: 5-level select tree (registers cannot be indexed dynamically)
+                  uint32_t s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+                  for (int x = 0; x < 16; ++x) s16[x] = (j & 16) ? r[16 + x] : r[x];
+#pragma unroll
+                  for (int x = 0; x < 8; ++x) s8[x] = (j & 8) ? s16[8 + x] : s16[x];
+#pragma unroll
+                  for (int x = 0; x < 4; ++x) s4[x] = (j & 4) ? s8[4 + x] : s8[x];
+#pragma unroll
+                  for (int x = 0; x < 2; ++x) s2[x] = (j & 2) ? s4[2 + x] : s4[x];
+                  const float sc = __uint_as_float((j & 1) ? s2[1] : s2[0]);
+                  const int64_t item = item0 + chunk * 32 + j;
+                  if (item_ok(P, q, item)) row_append(P, st, sc, item);   // full predicate (self / allow / exclusion lists)
+                }
+              }
+              warp_compact_if_needed(P, st, q, lane);
+            }
           }
         }
         // accumulator drained: hand it back to the MMA issuer
@@ -385,7 +458,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
       if (P.dump == nullptr) {
-        P.cand_cnt[static_cast<int64_t>(split) * P.b_pad + q] = st.cnt;
+        P.cand_cnt[slot] = st.cnt;
         if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
       }
     }
