@@ -80,7 +80,8 @@ class bb_query_batch(C.Structure):
 class bb_info(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("sm_count", C.c_int32), ("k_pad", C.c_int32),
                 ("cta_group", C.c_int32), ("launches", C.c_int64), ("last_units", C.c_int64),
-                ("last_candidates", C.c_int64), ("bytes_fp32", C.c_double), ("bytes_bf16", C.c_double),
+                ("last_candidates", C.c_int64), ("last_appends", C.c_int64), ("last_slow_chunks", C.c_int64),
+                ("last_compactions", C.c_int64), ("bytes_fp32", C.c_double), ("bytes_bf16", C.c_double),
                 ("scan_ms", C.c_double), ("scan_launches", C.c_int64)]
 
 

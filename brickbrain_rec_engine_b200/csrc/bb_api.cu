@@ -53,7 +53,7 @@ struct DevBuf {
 
 struct Workspace {
   std::mutex mu;
-  DevBuf q_f32, q_bf16, cand, cand_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid;
+  DevBuf q_f32, q_bf16, cand, cand_cnt, pub_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid;
   alignas(64) CUtensorMap tmap_q;
   const void* tmap_q_ptr = nullptr;
   int tmap_q_rows = 0;
@@ -341,12 +341,15 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     const size_t slots = static_cast<size_t>(plan.n_splits) * P.n_sub * plan.b_pad;
     BB_CUDA(h, w->cand.ensure(slots * kCap * sizeof(uint64_t)));
     BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
+    BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
+    BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
+    P.pub_cnt = static_cast<int32_t*>(w->pub_cnt.p);
     BB_CUDA(h, w->thr_g.ensure(static_cast<size_t>(plan.b_pad) * sizeof(uint32_t)));
     P.cand = static_cast<uint64_t*>(w->cand.p);
     P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
     P.thr_g = static_cast<uint32_t*>(w->thr_g.p);
     BB_CUDA(h, launch_fill_u32(P.thr_g, kOrdNegInf, plan.b_pad, stream));
-    BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, sizeof(unsigned long long), stream));
+    BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, 4 * sizeof(unsigned long long), stream));
     h->launches++;
   }
 
@@ -497,7 +500,7 @@ void bb_destroy(bb_handle* h) {
   cudaDeviceSynchronize();
   for (auto& kv : h->ws) {
     Workspace* w = kv.second;
-    for (DevBuf* b : {&w->q_f32, &w->q_bf16, &w->cand, &w->cand_cnt, &w->thr_g, &w->out_scores, &w->out_ids, &w->misc,
+    for (DevBuf* b : {&w->q_f32, &w->q_bf16, &w->cand, &w->cand_cnt, &w->pub_cnt, &w->thr_g, &w->out_scores, &w->out_ids, &w->misc,
                       &w->stage, &w->dump, &w->shared_valid})
       b->release();
     if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
@@ -529,9 +532,12 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->cta_group = h->cta_group;
   info->launches = h->launches.load();
   info->last_units = h->last_units.load();
-  unsigned long long c = 0;
-  BB_CUDA(h, cudaMemcpy(&c, h->stat_dev, sizeof(c), cudaMemcpyDeviceToHost));
-  info->last_candidates = static_cast<int64_t>(c);
+  unsigned long long c[4] = {0, 0, 0, 0};
+  BB_CUDA(h, cudaMemcpy(c, h->stat_dev, sizeof(c), cudaMemcpyDeviceToHost));
+  info->last_candidates = static_cast<int64_t>(c[0]);
+  info->last_appends = static_cast<int64_t>(c[1]);
+  info->last_slow_chunks = static_cast<int64_t>(c[2]);
+  info->last_compactions = static_cast<int64_t>(c[3]);
   const double rows = static_cast<double>(h->cfg.n_items);
   info->bytes_fp32 = h->cat_f32 ? rows * h->k_pad * 4.0 : 0.0;
   info->bytes_bf16 = h->cat_bf16 ? rows * h->k_pad * 2.0 : 0.0;

@@ -43,8 +43,8 @@ __device__ __forceinline__ int32_t key_id(uint64_t k) { return static_cast<int32
 
 // ---------------------------------------------------------------- warp bitonic sort (descending)
 // 32*EPL keys distributed as element e = i*32 + lane  (i = register index).
-template <int EPL>
-__device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[EPL], int lane) {
+template <int EPL, typename K = uint64_t>
+__device__ __forceinline__ void warp_sort_desc(K (&v)[EPL], int lane) {
 #pragma unroll
   for (int k = 2; k <= 32 * EPL; k <<= 1) {
 #pragma unroll
@@ -56,7 +56,7 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[EPL], int lane) {
           const int ip = i ^ ji;
           if (ip > i) {
             const bool desc = (((i << 5) & k) == 0);   // k >= 64 here: the bit lives in i
-            const uint64_t a = v[i], b = v[ip];
+            const K a = v[i], b = v[ip];
             const bool sw = desc ? (a < b) : (a > b);
             v[i] = sw ? b : a;
             v[ip] = sw ? a : b;
@@ -66,12 +66,12 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[EPL], int lane) {
 #pragma unroll
         for (int i = 0; i < EPL; ++i) {
           const int e = (i << 5) | lane;
-          const uint64_t a = v[i];
-          const uint64_t b = __shfl_xor_sync(kFull, a, j);
+          const K a = v[i];
+          const K b = __shfl_xor_sync(kFull, a, j);
           const bool lower = (lane & j) == 0;
           const bool desc = ((e & k) == 0);
           const bool keep_max = (lower == desc);
-          const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+          const K mx = a > b ? a : b, mn = a > b ? b : a;
           v[i] = keep_max ? mx : mn;
         }
       }
@@ -104,7 +104,8 @@ struct ScanParams {
   int32_t n_sub;          // buffers per (split, row): the tcgen05 epilogue uses one per column half
   uint64_t* cand;
   int32_t* cand_cnt;
-  uint32_t* thr_g;        // per-row shared running threshold (ordered bits), max over splits
+  int32_t* pub_cnt;       // per slot: number of SORTED keys at the front of the buffer (published at compaction)
+  uint32_t* thr_g;        // per-row shared running threshold (ordered bits), raised by every stream of the row
   // schedule
   int32_t n_qblocks;      // query blocks
   int32_t n_splits;       // catalog splits (units = n_qblocks * n_splits)
@@ -173,7 +174,7 @@ static __device__ __noinline__ bool item_ok(const ScanParams& P, int row, int64_
 }
 
 // ---------------------------------------------------------------- per-row candidate buffer
-// One thread owns a query row: `thr` is a lower bound of the row's k'-th best
+// One thread owns a (query row, stream): `thr` is a lower bound of the row's k'-th best
 // valid score, `cnt` the number of keys in its buffer.  A score passes when
 // score >= thr; passing + valid candidates are appended; when a buffer could
 // overflow the warp sorts it and keeps the best k_sel, which raises thr.
@@ -181,54 +182,136 @@ struct RowState {
   float thr;
   int cnt;
   uint64_t* buf;
+  int64_t slot;           // (split * n_sub + sub) * b_pad + row
 };
+
+__device__ __forceinline__ int32_t ld_acquire_s32(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // Warp-cooperative compaction of ONE row's buffer (all 32 lanes call with the
 // same buf / cnt).  Returns the new count; *new_thr gets the k_sel-th best score
-// (or -inf when fewer than k_sel candidates exist).
-__device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, int lane, float* new_thr) {
-  uint64_t v[kEpl];
+// (or -inf when fewer than k_sel candidates exist).  The sort network is sized to cnt.
+template <int EPL>
+__device__ __forceinline__ uint64_t warp_compact_n(uint64_t* buf, int cnt, int k_sel, int lane) {
+  uint64_t v[EPL];
 #pragma unroll
-  for (int i = 0; i < kEpl; ++i) {
+  for (int i = 0; i < EPL; ++i) {
     const int e = (i << 5) | lane;
     v[i] = (e < cnt) ? __ldcg(buf + e) : 0ull;
   }
-  warp_sort_desc<kEpl>(v, lane);
+  warp_sort_desc<EPL>(v, lane);
   const int kw = k_sel >> 5;
   uint64_t kth = 0;
 #pragma unroll
-  for (int i = 0; i < kEpl; ++i) {
+  for (int i = 0; i < EPL; ++i) {
     if (i < kw) {
       __stcg(buf + ((i << 5) | lane), v[i]);
       if (i == kw - 1) kth = v[i];
     }
   }
-  kth = __shfl_sync(kFull, kth, 31);
+  return __shfl_sync(kFull, kth, 31);
+}
+
+__device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, int lane, float* new_thr) {
+  uint64_t kth;
+  if (cnt <= 32) kth = warp_compact_n<1>(buf, cnt, k_sel, lane);
+  else if (cnt <= 64) kth = warp_compact_n<2>(buf, cnt, k_sel, lane);
+  else if (cnt <= 128) kth = warp_compact_n<4>(buf, cnt, k_sel, lane);
+  else kth = warp_compact_n<kEpl>(buf, cnt, k_sel, lane);
   *new_thr = (cnt >= k_sel) ? key_score(kth) : -INFINITY;
   __syncwarp();
   return cnt < k_sel ? cnt : k_sel;
 }
 
+// Cross-stream threshold refinement.  A query row is scanned by many independent streams (catalog splits x
+// column halves), each keeping its own sorted top-k' prefix.  If `need` streams each hold at least r keys
+// >= T then at least need*r >= k' valid items score >= T, so T is a valid lower bound of the row's k'-th best.
+// With n published streams the useful levels are the smallest r = 2^l with ceil(k'/r) <= n and the next two;
+// T_r = the ceil(k'/r)-th largest of the streams' r-th best keys and the bound is max_r T_r (r = k' is each
+// stream's own threshold).  This lets ~74 streams per row share a threshold close to the global one instead of
+// the max of their local ones.
+constexpr int kRefineSlots = 128;
+__device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, int row, int lane) {
+  const int n_slots = P.n_splits * P.n_sub;
+  if (n_slots <= 1) return 0u;
+  const int stride = (n_slots + kRefineSlots - 1) / kRefineSlots;
+  const int n_use = (n_slots + stride - 1) / stride;
+  constexpr int kPer = kRefineSlots / 32;
+  int c[kPer];
+  int64_t slot[kPer];
+  int n_pub = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int s = (lane + 32 * i) * stride;
+    c[i] = 0;
+    slot[i] = 0;
+    if (lane + 32 * i < n_use && s < n_slots) {
+      slot[i] = static_cast<int64_t>(s) * P.b_pad + row;
+      c[i] = __ldcg(P.pub_cnt + slot[i]);
+    }
+    n_pub += __popc(__ballot_sync(kFull, c[i] > 0));
+  }
+  __threadfence();                                  // keys read below are at least as new as the counts read above
+  if (n_pub == 0) return 0u;
+  int r0 = 2;
+  while (r0 < P.k_sel && (P.k_sel + r0 - 1) / r0 > n_pub) r0 <<= 1;
+  uint32_t best = 0u;
+#pragma unroll 1
+  for (int l = 0; l < 3; ++l) {
+    const int r = r0 << l;
+    if (r >= P.k_sel) break;                        // the r = k' level is the stream's own threshold
+    const int need = (P.k_sel + r - 1) / r;
+    uint32_t v[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i)
+      v[i] = (c[i] >= r) ? static_cast<uint32_t>(__ldcg(P.cand + slot[i] * kCap + (r - 1)) >> 32) : 0u;
+    warp_sort_desc<kPer, uint32_t>(v, lane);
+    const int e = need - 1;                         // element e lives in register e>>5 of lane e&31
+    uint32_t t = 0u;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i)
+      if ((e >> 5) == i) t = v[i];
+    t = __shfl_sync(kFull, t, e & 31);
+    best = t > best ? t : best;
+  }
+  return best;
+}
+
 // After a group of <= 32 appends per lane: compact every row of this warp whose
-// buffer could overflow on the next group, and publish the raised threshold.
-__device__ __forceinline__ void warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane) {
+// buffer could overflow on the next group, publish its sorted prefix, and raise the
+// row's shared threshold (own k'-th best and the cross-stream refinement).
+// `force_mask`: lanes whose buffer is compacted regardless of fill (unit end: leave a sorted, published prefix).
+__device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane,
+                                                      unsigned force_mask = 0u) {
   __syncwarp();
-  unsigned need = __ballot_sync(kFull, st.cnt > kCap - 32);
+  unsigned need = __ballot_sync(kFull, st.cnt > kCap - 32) | force_mask;
+  const int n_compactions = __popc(need);
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
     uint64_t* b = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(st.buf), src));
     const int c = __shfl_sync(kFull, st.cnt, src);
+    const int src_row = __shfl_sync(kFull, row, src);
+    const long long src_slot = __shfl_sync(kFull, static_cast<long long>(st.slot), src);
     float nt;
     const int nc = warp_compact(b, c, P.k_sel, lane, &nt);
+    __threadfence();                                // sorted keys are visible before the count that advertises them
+    if (lane == 0) atomicMax(P.pub_cnt + src_slot, nc);
+    const uint32_t refined = warp_refine_threshold(P, src_row, lane);
     if (lane == src) {
       st.cnt = nc;
-      if (nt > st.thr) {
-        st.thr = nt;
-        atomicMax(P.thr_g + row, f2ord(nt));
+      uint32_t o = f2ord(nt);
+      o = refined > o ? refined : o;
+      if (o > f2ord(st.thr)) {
+        st.thr = ord2f(o);
+        atomicMax(P.thr_g + row, o);
       }
     }
   }
+  return n_compactions;
 }
 
 __device__ __forceinline__ void row_append(const ScanParams& P, RowState& st, float score, int64_t item) {

@@ -61,7 +61,8 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
   RowState st;
   st.thr = (warp < 4 && own_row < P.n_queries) ? -INFINITY : INFINITY;
   st.cnt = 0;
-  st.buf = P.cand + (static_cast<int64_t>(split) * P.b_pad + (warp < 4 ? own_row : 0)) * kCap;
+  st.slot = static_cast<int64_t>(split) * P.n_sub * P.b_pad + (warp < 4 ? own_row : 0);
+  st.buf = P.cand + st.slot * kCap;
 
   const int n_slabs = P.k_pad / XK;
   for (int t = t0; t < t1; ++t) {
@@ -151,7 +152,9 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
   }
 
   if (warp < 4 && P.dump == nullptr) {
-    P.cand_cnt[static_cast<int64_t>(split) * P.b_pad + own_row] = st.cnt;
+    const unsigned fresh = __ballot_sync(kFull, own_row < P.n_queries && st.cnt > 0);
+    warp_compact_if_needed(P, st, own_row, lane, fresh);
+    P.cand_cnt[st.slot] = st.cnt;
     if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
   }
 }

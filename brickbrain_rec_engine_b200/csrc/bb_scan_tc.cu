@@ -75,7 +75,9 @@ __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive: a cluster-scope release would
+  // fence every outstanding global candidate store of the warp (ERRBAR) once per tile
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -329,6 +331,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t acc_empty_leader_base = (CG == 2) ? mapa_u32(smem_u32(bar_acc_empty), 0) : smem_u32(bar_acc_empty);
     const bool use_cons = P.cons != nullptr && P.shared_valid == nullptr;
+    unsigned stat_appends = 0, stat_slow = 0, stat_compact = 0;   // per-thread / per-warp counters (debug statistics)
     for (int u = group; u < n_units; u += n_groups) {
       const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
       int t0, t1;
@@ -340,8 +343,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       int pmin = INT32_MIN, ymin = -32768;
       unsigned prange = 0xffffffffu, yrange = 0xffffu;
       bool has_theme = false, dead = !q_valid;
+      bool needs_full = false;                       // allow bitmap / exclusion lists / wide theme sets -> item_ok()
+      int64_t self_local = -1;                       // local row excluded for this query (-1 none)
+      if (q_valid && P.self_id != nullptr) {
+        const int64_t sl = static_cast<int64_t>(__ldg(P.self_id + q)) - P.id_offset;
+        if (sl >= 0 && sl < P.n_items) self_local = sl;
+      }
       if (q_valid && P.cons != nullptr) {
         const bb_constraint c = P.cons[static_cast<int64_t>(q) * P.cons_stride];
+        needs_full = c.allow_bitmap >= 0 || c.excl_list[0] >= 0 || c.excl_list[1] >= 0 || c.excl_list[2] >= 0 ||
+                     (c.theme_set >= 0 && P.theme_words > 32);
         if ((c.flags & BB_C_ALWAYS_FALSE) || c.parts_max < c.parts_min || c.year_max < c.year_min) dead = true;
         pmin = c.parts_min;
         prange = static_cast<unsigned>(c.parts_max) - static_cast<unsigned>(c.parts_min);
@@ -359,8 +370,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       st.cnt = 0;
       const int64_t slot = (static_cast<int64_t>(split) * P.n_sub + half) * P.b_pad + q;
       st.buf = P.cand + slot * kCap;
+      st.slot = slot;
+      const bool share_thr = !dead && P.dump == nullptr;
+      uint32_t thr_next = share_thr ? __ldcg(P.thr_g + q) : 0u;   // shared threshold, fetched one tile ahead
       for (int t = t0; t < t1; ++t) {
-        if (!dead && P.dump == nullptr) st.thr = fmaxf(st.thr, ord2f(__ldcg(P.thr_g + q)));
+        if (share_thr) {
+          st.thr = fmaxf(st.thr, ord2f(thr_next));
+          thr_next = __ldcg(P.thr_g + q);
+        }
         mbar_wait(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols;
@@ -370,6 +387,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (P.debug_flags & 2) break;
           uint32_t r[32];
           tmem_ld32(taddr + chunk * 32, r);
+          // this lane also "owns" one column of the chunk: fetch and unpack its metadata while the TMEM load is
+          // in flight (only batches with per-row constraints pay for it)
+          const int64_t col_item = item0 + chunk * 32 + lane;
+          uint4 cm = make_uint4(0u, 0u, 0u, 0u);
+          if (use_cons) {
+            int2 mt = make_int2(0, 0);
+            if (col_item < P.n_items) mt = __ldg(P.meta + col_item);
+            const int c_theme = mt.y >> 16;
+            cm.x = static_cast<unsigned>(mt.x);                                                     // num_parts
+            cm.y = static_cast<unsigned>(static_cast<int>(static_cast<int16_t>(mt.y & 0xffff)));   // year
+            cm.z = static_cast<unsigned>(c_theme >= 0 ? min(c_theme >> 5, 31) : 0) * 128u;          // theme word offset
+            cm.w = (c_theme >= 0 && c_theme < 1024) ? (1u << (c_theme & 31)) : 0u;                  // theme bit (0 = NULL)
+          }
           tmem_ld_wait();
           if (P.dump != nullptr) {
             if (q_valid) {
@@ -386,41 +416,31 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
           if (__any_sync(kFull, m >= st.thr) && !(P.debug_flags & 1)) {
             // ---- slow path, entered only when some row of this warp has a score >= its threshold
+            ++stat_slow;
             unsigned pm = 0;                                   // per row: columns whose score passes
 #pragma unroll
             for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= st.thr) ? (1u << j) : 0u;
-            const int64_t col_item = item0 + chunk * 32 + lane;   // this lane also "owns" one column's metadata
             pm &= ~__ballot_sync(kFull, col_item >= P.n_items);
             if (P.shared_valid != nullptr) {
               // one constraint shared by the whole batch: its validity bitmap was built by the mask kernel
               pm &= __ldg(P.shared_valid + ((item0 + chunk * 32) >> 5));
             } else if (use_cons) {
-              unsigned cols = __reduce_or_sync(kFull, pm);     // columns with at least one passing row (uniform)
-              if (cols != 0u) {
-                // column owners unpack their item's metadata once; rows then read it as a shared-memory broadcast
-                int2 mt = make_int2(0, 0);
-                if (col_item < P.n_items) mt = __ldg(P.meta + col_item);
-                const int c_theme = mt.y >> 16;
-                uint4 cm;
-                cm.x = static_cast<unsigned>(mt.x);                                            // num_parts
-                cm.y = static_cast<unsigned>(static_cast<int>(static_cast<int16_t>(mt.y & 0xffff)));   // year
-                cm.z = static_cast<unsigned>(c_theme >= 0 ? min(c_theme >> 5, 31) : 0) * 128u;  // theme word offset
-                cm.w = (c_theme >= 0 && c_theme < 1024) ? (1u << (c_theme & 31)) : 0u;          // theme bit (0 = NULL)
-                __syncwarp();
-                colmeta_w[lane] = cm;
-                __syncwarp();
-                unsigned vm = 0;
-                while (cols != 0u) {
-                  const int j = __ffs(cols) - 1;
-                  cols &= cols - 1;
-                  const uint4 c4 = colmeta_w[j];
-                  bool ok = (c4.x - static_cast<unsigned>(pmin) <= prange) &&
-                            (c4.y - static_cast<unsigned>(ymin) <= yrange);
-                  if (any_theme) ok = ok && (!has_theme || (theme_row[c4.z] & c4.w) != 0u);
-                  vm |= ok ? (1u << j) : 0u;
-                }
-                pm &= vm;
+              // column owners publish their item's unpacked metadata (prefetched above) in shared memory;
+              // every row then checks only ITS OWN passing columns (trip count = max passes of one row)
+              __syncwarp();
+              colmeta_w[lane] = cm;
+              __syncwarp();
+              unsigned todo = pm, vm = 0;
+              while (todo != 0u) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint4 c4 = colmeta_w[j];
+                bool ok = (c4.x - static_cast<unsigned>(pmin) <= prange) && (c4.y - static_cast<unsigned>(ymin) <= yrange);
+                if (has_theme) ok = ok && (theme_row[c4.z] & c4.w) != 0u;
+                vm |= ok ? (1u << j) : 0u;
               }
+              pm = vm;
+              __syncwarp();
             }
             if (__any_sync(kFull, pm != 0u)) {
               // ---- rare: a masked-in candidate exists
@@ -440,10 +460,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                   for (int x = 0; x < 2; ++x) s2[x] = (j & 2) ? s4[2 + x] : s4[x];
                   const float sc = __uint_as_float((j & 1) ? s2[1] : s2[0]);
                   const int64_t item = item0 + chunk * 32 + j;
-                  if (item_ok(P, q, item)) row_append(P, st, sc, item);   // full predicate (self / allow / exclusion lists)
+                  // cheap predicates were applied above; only rows with allow bitmaps / exclusion lists pay the call
+                  if (item != self_local && (!needs_full || item_ok(P, q, item))) {
+                    row_append(P, st, sc, item);
+                    ++stat_appends;
+                  }
                 }
               }
-              warp_compact_if_needed(P, st, q, lane);
+              stat_compact += warp_compact_if_needed(P, st, q, lane);
             }
           }
         }
@@ -458,8 +482,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (acc == 0) acc_phase ^= 1;
       }
       if (P.dump == nullptr) {
+        // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units
+        // that scan this row later start from everything this stream has learnt
+        const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt > 0);
+        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh);
         P.cand_cnt[slot] = st.cnt;
         if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
+      }
+    }
+    if (P.stat_candidates != nullptr && P.dump == nullptr) {
+      const unsigned a = __reduce_add_sync(kFull, stat_appends);
+      if (lane == 0) {
+        atomicAdd(P.stat_candidates + 1, static_cast<unsigned long long>(a));
+        atomicAdd(P.stat_candidates + 2, static_cast<unsigned long long>(stat_slow));
+        atomicAdd(P.stat_candidates + 3, static_cast<unsigned long long>(stat_compact));
       }
     }
   }

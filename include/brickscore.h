@@ -118,7 +118,10 @@ typedef struct bb_info {
   int32_t cta_group;        /* 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTA */
   int64_t launches;         /* kernels launched by this handle so far */
   int64_t last_units;       /* (query block, catalog split) work units of the last search */
-  int64_t last_candidates;  /* candidates that survived the running threshold in the last search (debug) */
+  int64_t last_candidates;  /* candidates left in the buffers at the end of the last scan (debug) */
+  int64_t last_appends;     /* candidates appended by the last scan's epilogue */
+  int64_t last_slow_chunks; /* 32-column chunks that entered the epilogue slow path */
+  int64_t last_compactions; /* candidate-buffer compactions (warp sorts) */
   double bytes_fp32, bytes_bf16; /* resident operand bytes */
   double scan_ms;           /* device time of the scan kernels since bb_set_profiling(h, 1) (CUDA events) */
   int64_t scan_launches;    /* scan kernel launches covered by scan_ms */

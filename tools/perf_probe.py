@@ -49,14 +49,15 @@ def child(n, b, k, cons):
         ms = i["scan_ms"] / i["scan_launches"]
         tf = 2.0 * b * n * 448 / (ms * 1e-3) / 1e12
         print(f"flags={os.environ.get('BB_DEBUG_FLAGS','0')} cg={i['cta_group']} cons={cons} n={n} b={b} k={k}: scan {ms:.2f} ms = {tf:.1f} TFLOP/s "
-              f"units={i['last_units']} cands={i['last_candidates']}", flush=True)
+              f"units={i['last_units']} cands={i['last_candidates']} appends={i['last_appends']} slow_chunks={i['last_slow_chunks']} "
+              f"compactions={i['last_compactions']}", flush=True)
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         child(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
         sys.exit(0)
-    sizes = sys.argv[1:] if False else ["2000000", "10000000"]
+    sizes = ["10000000"]
     for n in sizes:
         for cg in ("2",):
             for flags in ("0", "1"):
