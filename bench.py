@@ -36,7 +36,7 @@ UNIT = "queries/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--n-items", type=int, default=10_000_000)
@@ -62,7 +62,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -82,7 +82,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed window: earlier samples (warm-up) are dropped."""
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -94,7 +98,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, l in self.lines:
+            if ts < t_mark:
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 9:
                 continue
@@ -254,16 +261,17 @@ def run_ours(args):
         return float(t.item())
 
     # ---------------- device-resident timing (`value`)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs a moment to start: launch it before the warm-up
     for i in range(args.warmup):
         step_device(i)
     barrier()
     eng.set_profiling(True)
     launches0 = eng.info()["launches"]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for i in range(args.steps):
         step_device(i)

@@ -206,7 +206,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                const ScanParams P, const int n_groups) {
   using C = Cfg<CG>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024 B alignment (128B swizzle atoms) by pointer arithmetic on the __shared__ array, so that the compiler keeps
+  // the shared address space (integer round-trips degrade every later access to generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* smem_a = smem;
   unsigned char* smem_b = smem + kTcMaxKBlocks * kAkbBytes;
   uint4* smem_colmeta = reinterpret_cast<uint4*>(smem_b + C::kStages * C::kBStageBytes);
