@@ -219,7 +219,7 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   if (splits > p.n_tiles) splits = p.n_tiles;
   if (splits < 1) splits = 1;
   // bound candidate memory (2 KB per (split, row)) to 2 GiB
-  const long long max_splits = (2ll << 30) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? 2 : 1));
+  const long long max_splits = (2ll << 30) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? kTcSubStreams : 1));
   if (splits > max_splits) splits = max_splits > 0 ? max_splits : 1;
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
@@ -328,7 +328,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.n_qblocks = plan.n_qblocks;
   P.n_splits = plan.n_splits;
   P.n_tiles = plan.n_tiles;
-  P.n_sub = tc ? 2 : 1;
+  P.n_sub = tc ? kTcSubStreams : 1;
   P.tile_items = plan.tile_items;
   P.dump = dump;
   P.stat_candidates = h->stat_dev;

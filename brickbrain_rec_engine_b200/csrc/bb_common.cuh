@@ -285,7 +285,7 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
 // row's shared threshold (own k'-th best and the cross-stream refinement).
 // `force_mask`: lanes whose buffer is compacted regardless of fill (unit end: leave a sorted, published prefix).
 __device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane,
-                                                      unsigned force_mask = 0u) {
+                                                      unsigned force_mask = 0u, bool refine = true) {
   __syncwarp();
   unsigned need = __ballot_sync(kFull, st.cnt > kCap - 32) | force_mask;
   const int n_compactions = __popc(need);
@@ -300,7 +300,7 @@ __device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowSt
     const int nc = warp_compact(b, c, P.k_sel, lane, &nt);
     __threadfence();                                // sorted keys are visible before the count that advertises them
     if (lane == 0) atomicMax(P.pub_cnt + src_slot, nc);
-    const uint32_t refined = warp_refine_threshold(P, src_row, lane);
+    const uint32_t refined = refine ? warp_refine_threshold(P, src_row, lane) : 0u;
     if (lane == src) {
       st.cnt = nc;
       uint32_t o = f2ord(nt);

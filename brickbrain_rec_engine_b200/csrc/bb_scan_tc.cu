@@ -14,8 +14,8 @@
 //   * work unit = (query block, catalog split); units are dealt round-robin to groups.
 //
 // Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA),
-// 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (TMEM lane quarter = warp % 4; the two
-// warps of a quarter split the tile's 256 columns; one thread per (query row, column half)).
+// 2 = TMEM allocator, 3 = idle, 4..19 = epilogue (TMEM lane quarter = warp % 4; the four
+// warps of a quarter split the tile's 256 columns; one thread per (query row, column slice) = one stream).
 //
 // Roofline: tensor core.  2*128*256*k_pad flop per CTA tile; catalog bytes
 // 256*k_pad*2 per group tile.
@@ -33,7 +33,7 @@ constexpr int kAkbBytes = 128 * 128;        // resident query k-block: 128 rows 
 constexpr int kUmmaK = 16;
 constexpr int kAccCols = 256;               // fp32 accumulator columns per tile
 constexpr int kTmemCols = 512;              // two accumulators
-constexpr int kEpiWarps = 8;                // two warps per TMEM lane quarter, each scans half of the tile's columns
+constexpr int kEpiWarps = 4 * kTcSubStreams; // kTcSubStreams warps per TMEM lane quarter, each scans a column slice of every tile
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerWarp = (kAccCols / 32) / (kEpiWarps / 4);
 constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata of the 32 columns of a chunk
@@ -326,7 +326,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   } else if (warp >= 4) {
     // ============================== epilogue: mask + running-threshold top-k ==============================
     const int ew = warp & 3;                        // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;               // which column half of every tile this warp scans
+    const int half = (warp - 4) >> 2;               // which column slice of every tile this warp scans
     const int row_in_cta = ew * 32 + lane;
     uint4* colmeta_w = smem_colmeta + (warp - 4) * 32;
     uint32_t* theme_row = smem_theme + row_in_cta;  // this row's allowed-theme words at [w * 128]
@@ -487,7 +487,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units
         // that scan this row later start from everything this stream has learnt
         const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt > 0);
-        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh);
+        // (one of the row's column-slice streams refines; the others only sort + publish)
+        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, half == 0);
         P.cand_cnt[slot] = st.cnt;
         if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
       }
