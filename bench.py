@@ -45,6 +45,8 @@ def parse():
     p.add_argument("--dim", type=int, default=384)
     p.add_argument("--cf-dim", type=int, default=64)
     p.add_argument("--precision", default="bf16_rescore", choices=["fp32", "bf16", "bf16_rescore"])
+    p.add_argument("--constraint-form", default="indexed", choices=["indexed", "per-query"],
+                   help="indexed: distinct constraint sets + per-query index (class bitmaps); per-query: one descriptor per query")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-items", type=int, default=1_000_000)
     p.add_argument("--cpu-sample-queries", type=int, default=1024)
@@ -189,6 +191,11 @@ def run_ours(args):
     eng = ScoringEngine(hi - lo, d, f, device=local, id_offset=lo, k_max=128, max_batch=b)
     descs, theme_bitmaps, themes = scenario_descriptors(b)
     eng.set_theme_sets(theme_bitmaps)
+    # queries carry (index into) the batch's distinct constraint sets; --distinct-constraints per-query disables it
+    if args.constraint_form == "indexed":
+        distinct, cons_index = ScoringEngine.dedupe_constraints(descs)
+    else:
+        distinct, cons_index = descs, np.arange(b, dtype=np.int32)
     theme_ids = torch.tensor(sorted(themes), device=dev, dtype=torch.int32)
     gmu = torch.Generator(device=dev).manual_seed(1234)
     mu = torch.nn.functional.normalize(torch.randn(d, device=dev, generator=gmu), dim=0)
@@ -208,10 +215,13 @@ def run_ours(args):
         q = torch.nn.functional.normalize(0.8 * mu.cpu()[None, :] + 0.6 * q, dim=1) * 3.0       # un-normalized on purpose
         u = torch.randn(b, f, generator=g) / (f ** 0.5)
         self_id = torch.randint(0, n, (b,), generator=g, dtype=torch.int32)
-        cons = torch.from_numpy(descs.view(np.uint8).reshape(b, -1).copy())
-        hq = dict(q=q.pin_memory(), u=u.pin_memory(), self_id=self_id.pin_memory(), cons=cons.pin_memory())
+        cons = torch.from_numpy(distinct.view(np.uint8).reshape(distinct.shape[0], -1).copy())
+        cidx = torch.from_numpy(cons_index.copy())
+        hq = dict(q=q.pin_memory(), u=u.pin_memory(), self_id=self_id.pin_memory(), cons=cons.pin_memory(),
+                  cidx=cidx.pin_memory())
         host.append(hq)
         devq.append({kk: vv.to(dev) for kk, vv in hq.items()})
+    indexed = args.constraint_form == "indexed"
     out_s = torch.empty((b, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((b, k), dtype=torch.int32, device=dev)
     gather_s = torch.empty((world, b, k), dtype=torch.float32, device=dev) if world > 1 else None
@@ -222,7 +232,8 @@ def run_ours(args):
     def step_device(i):
         qd = devq[i & 1]
         eng.search(k, q_emb=qd["q"], q_cf=qd["u"], w_content=0.4, w_cf=0.6, constraints=qd["cons"],
-                   self_id=qd["self_id"], precision=args.precision, out=(out_s, out_i))
+                   constraint_index=qd["cidx"] if indexed else None, self_id=qd["self_id"], precision=args.precision,
+                   out=(out_s, out_i))
         if world > 1:
             dist.all_gather_into_tensor(gather_s.view(-1), out_s.view(-1))
             dist.all_gather_into_tensor(gather_i.view(-1), out_i.view(-1))
@@ -233,13 +244,14 @@ def run_ours(args):
         """The user-facing call with HOST buffers: pinned inputs are copied in by bb_search, the result is read back."""
         qh = host[i & 1]
         cons_np = qh["cons"].numpy().view(L.CONSTRAINT_DTYPE).reshape(-1)
+        cidx_np = qh["cidx"].numpy() if indexed else None
         if world == 1:
             s, ids = eng.search(k, q_emb=qh["q"].numpy(), q_cf=qh["u"].numpy(), w_content=0.4, w_cf=0.6,
-                                constraints=cons_np, self_id=qh["self_id"].numpy(), precision=args.precision,
-                                out=(host_out_s.numpy(), host_out_i.numpy()))
+                                constraints=cons_np, constraint_index=cidx_np, self_id=qh["self_id"].numpy(),
+                                precision=args.precision, out=(host_out_s.numpy(), host_out_i.numpy()))
             return s, ids
         eng.search(k, q_emb=qh["q"].numpy(), q_cf=qh["u"].numpy(), w_content=0.4, w_cf=0.6, constraints=cons_np,
-                   self_id=qh["self_id"].numpy(), precision=args.precision, out=(out_s, out_i))
+                   constraint_index=cidx_np, self_id=qh["self_id"].numpy(), precision=args.precision, out=(out_s, out_i))
         dist.all_gather_into_tensor(gather_s.view(-1), out_s.view(-1))
         dist.all_gather_into_tensor(gather_i.view(-1), out_i.view(-1))
         ms, mi = eng.merge_topk(gather_s, gather_i, k)
@@ -295,7 +307,7 @@ def run_ours(args):
         step_e2e(i)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    h2d = b * (d + f) * 4 + b * 4 + b * L.CONSTRAINT_DTYPE.itemsize
+    h2d = b * (d + f) * 4 + b * 4 + distinct.shape[0] * L.CONSTRAINT_DTYPE.itemsize + (b * 4 if indexed else 0)
     d2h = b * k * 8
 
     if rank != 0:
@@ -317,10 +329,12 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
         "config": {"workload": f"config4: {n} items x ({d}+{f}) {('bf16' if args.precision != 'fp32' else 'fp32')} catalog, "
-                               f"batch {b} hybrid queries (0.4 content cosine + 0.6 CF dot), per-query hard-constraint "
-                               f"descriptors (light/medium/heavy/none mix), self exclusion, top-{k}",
+                               f"batch {b} hybrid queries (0.4 content cosine + 0.6 CF dot), per-query hard constraints "
+                               f"(light/medium/heavy/none mix of the reference's scenarios; passed as "
+                               f"{distinct.shape[0]} constraint sets" + (" + per-query index" if indexed else "") +
+                               f"), self exclusion, top-{k}",
                    "n_items": n, "batch": b, "k": k, "dim": d, "cf_dim": f, "precision": args.precision,
-                   "parallelism": f"row-sharded catalog x{world}" + (" + NCCL all-gather top-k merge" if world > 1 else ""),
+                   "constraint_form": args.constraint_form, "parallelism": f"row-sharded catalog x{world}" + (" + NCCL all-gather top-k merge" if world > 1 else ""),
                    "l2_policy": f"catalog shard ({(hi - lo) * (d + f) * 2 / 1e9:.2f} GB bf16) is larger than L2 (126 MB); "
                                 "query batches alternate"},
         "clocks": clocks,

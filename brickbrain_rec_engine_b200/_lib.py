@@ -73,7 +73,7 @@ class bb_query_batch(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_queries", C.c_int32), ("q_emb", C.c_void_p),
                 ("q_item", C.c_void_p), ("q_cf", C.c_void_p), ("w_content", C.c_void_p), ("w_cf", C.c_void_p),
                 ("w_content_all", C.c_float), ("w_cf_all", C.c_float), ("constraints", C.c_void_p),
-                ("n_constraints", C.c_int32), ("self_id", C.c_void_p), ("precision", C.c_int32),
+                ("n_constraints", C.c_int32), ("constraint_index", C.c_void_p), ("self_id", C.c_void_p), ("precision", C.c_int32),
                 ("flags", C.c_uint32)]
 
 
@@ -81,7 +81,8 @@ class bb_info(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("sm_count", C.c_int32), ("k_pad", C.c_int32),
                 ("cta_group", C.c_int32), ("launches", C.c_int64), ("last_units", C.c_int64),
                 ("last_candidates", C.c_int64), ("last_appends", C.c_int64), ("last_slow_chunks", C.c_int64),
-                ("last_compactions", C.c_int64), ("bytes_fp32", C.c_double), ("bytes_bf16", C.c_double),
+                ("last_compactions", C.c_int64), ("mma_wait_epilogue_cycles", C.c_int64),
+                ("mma_wait_tma_cycles", C.c_int64), ("mma_total_cycles", C.c_int64), ("bytes_fp32", C.c_double), ("bytes_bf16", C.c_double),
                 ("scan_ms", C.c_double), ("scan_launches", C.c_int64)]
 
 

@@ -251,8 +251,15 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   if ((q->q_emb != nullptr || q->q_item != nullptr) && h->cfg.dim == 0)
     return fail(h, BB_ERR_INVALID, "content query given but catalog has dim=0");
   if (q->q_cf != nullptr && h->cfg.cf_dim == 0) return fail(h, BB_ERR_INVALID, "CF query given but catalog has cf_dim=0");
-  if (q->n_constraints != 0 && q->n_constraints != 1 && q->n_constraints != B)
-    return fail(h, BB_ERR_INVALID, "n_constraints must be 0, 1 or n_queries");
+  if (q->constraint_index == nullptr && q->n_constraints != 0 && q->n_constraints != 1 && q->n_constraints != B)
+    return fail(h, BB_ERR_INVALID, "n_constraints must be 0, 1 or n_queries (or any count with constraint_index)");
+  if (q->constraint_index != nullptr && q->n_constraints <= 0)
+    return fail(h, BB_ERR_INVALID, "constraint_index given but n_constraints <= 0");
+  if (q->constraint_index != nullptr && !is_device_ptr(q->constraint_index)) {
+    for (int i = 0; i < B; ++i)
+      if (q->constraint_index[i] < 0 || q->constraint_index[i] >= q->n_constraints)
+        return fail(h, BB_ERR_INVALID, "constraint_index[%d] = %d out of range", i, q->constraint_index[i]);
+  }
   if (q->n_constraints != 0 && q->constraints == nullptr) return fail(h, BB_ERR_INVALID, "constraints is NULL");
 
   plan = make_plan(h, B, tc);
@@ -278,8 +285,9 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   st.account(q->w_cf, sizeof(float) * B);
   st.account(q->constraints, sizeof(bb_constraint) * q->n_constraints);
   st.account(q->self_id, sizeof(int32_t) * B);
+  st.account(q->constraint_index, sizeof(int32_t) * B);
   BB_CUDA(h, w->stage.ensure(st.need + 256));
-  const void *d_emb, *d_item, *d_cf, *d_wc, *d_wf, *d_cons, *d_self;
+  const void *d_emb, *d_item, *d_cf, *d_wc, *d_wf, *d_cons, *d_self, *d_cidx;
   BB_CUDA(h, st.get(q->q_emb, sizeof(float) * B * D, &d_emb));
   BB_CUDA(h, st.get(q->q_item, sizeof(int32_t) * B, &d_item));
   BB_CUDA(h, st.get(q->q_cf, sizeof(float) * B * F, &d_cf));
@@ -287,6 +295,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   BB_CUDA(h, st.get(q->w_cf, sizeof(float) * B, &d_wf));
   BB_CUDA(h, st.get(q->constraints, sizeof(bb_constraint) * q->n_constraints, &d_cons));
   BB_CUDA(h, st.get(q->self_id, sizeof(int32_t) * B, &d_self));
+  BB_CUDA(h, st.get(q->constraint_index, sizeof(int32_t) * B, &d_cidx));
 
   // ---- query operands
   const size_t qf_bytes = sizeof(float) * static_cast<size_t>(plan.b_pad) * KP;
@@ -317,7 +326,8 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.k_pad = KP;
   P.k_sel = k_sel;
   P.cons = static_cast<const bb_constraint*>(d_cons);
-  P.cons_stride = (q->n_constraints == B && B > 1) ? 1 : 0;
+  P.cons_stride = (q->constraint_index == nullptr && q->n_constraints == B && B > 1) ? 1 : 0;
+  P.cons_index = static_cast<const int32_t*>(d_cidx);
   P.self_id = static_cast<const int32_t*>(d_self);
   P.theme_sets = h->theme_sets;
   P.theme_words = h->theme_words;
@@ -349,22 +359,26 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
     P.thr_g = static_cast<uint32_t*>(w->thr_g.p);
     BB_CUDA(h, launch_fill_u32(P.thr_g, kOrdNegInf, plan.b_pad, stream));
-    BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, 4 * sizeof(unsigned long long), stream));
+    P.wave_counter = reinterpret_cast<uint32_t*>(h->stat_dev + 7);
+    BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, 8 * sizeof(unsigned long long), stream));
     h->launches++;
   }
 
-  // ---- one constraint shared by the whole batch: evaluate it once per item with the mask kernel (K3); the scan
-  //      epilogue then masks a 32-item chunk with a single word of the bitmap
-  if (tc && dump == nullptr && q->n_constraints == 1 && B > 1) {
+  // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
+  //      set once per item with the mask kernel (K3); the scan epilogue then masks a 32-item chunk of a row with
+  //      one word of its set's bitmap
+  const int n_classes = (q->n_constraints == 1 && B > 1) ? 1 : (q->constraint_index != nullptr ? q->n_constraints : 0);
+  if (tc && dump == nullptr && n_classes >= 1 && n_classes <= 64) {
     const int64_t words = (h->cfg.n_items + 31) / 32;
-    BB_CUDA(h, w->shared_valid.ensure(static_cast<size_t>(words) * sizeof(uint32_t) + 64));
-    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(w->shared_valid.p) +
-                                                                     static_cast<size_t>(words) * sizeof(uint32_t));
-    cnt = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(cnt) + 7) & ~static_cast<uintptr_t>(7));
-    BB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), stream));
-    BB_CUDA(h, launch_mask(P, 1, static_cast<uint32_t*>(w->shared_valid.p), cnt, stream));
+    const size_t bm_bytes = static_cast<size_t>(n_classes) * words * sizeof(uint32_t);
+    BB_CUDA(h, w->shared_valid.ensure(bm_bytes + 8 * static_cast<size_t>(n_classes) + 64));
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(static_cast<unsigned char*>(w->shared_valid.p) + bm_bytes) + 7) & ~static_cast<uintptr_t>(7));
+    BB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * n_classes, stream));
+    BB_CUDA(h, launch_mask(P, n_classes, static_cast<uint32_t*>(w->shared_valid.p), cnt, stream));
     h->launches++;
-    P.shared_valid = static_cast<const uint32_t*>(w->shared_valid.p);
+    P.class_valid = static_cast<const uint32_t*>(w->shared_valid.p);
+    P.class_words = words;
   }
 
   // ---- scan
@@ -532,12 +546,15 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->cta_group = h->cta_group;
   info->launches = h->launches.load();
   info->last_units = h->last_units.load();
-  unsigned long long c[4] = {0, 0, 0, 0};
+  unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   BB_CUDA(h, cudaMemcpy(c, h->stat_dev, sizeof(c), cudaMemcpyDeviceToHost));
   info->last_candidates = static_cast<int64_t>(c[0]);
   info->last_appends = static_cast<int64_t>(c[1]);
   info->last_slow_chunks = static_cast<int64_t>(c[2]);
   info->last_compactions = static_cast<int64_t>(c[3]);
+  info->mma_wait_epilogue_cycles = static_cast<int64_t>(c[4]);
+  info->mma_wait_tma_cycles = static_cast<int64_t>(c[5]);
+  info->mma_total_cycles = static_cast<int64_t>(c[6]);
   const double rows = static_cast<double>(h->cfg.n_items);
   info->bytes_fp32 = h->cat_f32 ? rows * h->k_pad * 4.0 : 0.0;
   info->bytes_bf16 = h->cat_bf16 ? rows * h->k_pad * 2.0 : 0.0;

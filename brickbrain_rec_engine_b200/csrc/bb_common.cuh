@@ -99,7 +99,9 @@ struct ScanParams {
   int64_t allow_words;
   const int64_t* excl_off;
   const int32_t* excl_ids;
-  const uint32_t* shared_valid;   // validity bitmap of the single shared constraint (built by the mask kernel) or nullptr
+  const int32_t* cons_index;      // per-row index into cons[] (distinct constraint sets) or nullptr
+  const uint32_t* class_valid;    // per distinct constraint set: validity bitmap over local rows (mask kernel) or nullptr
+  int64_t class_words;            // words per class bitmap
   // candidate buffers: slot = (split * n_sub + sub) * b_pad + row; cand[slot * kCap + i], cnt[slot]
   int32_t n_sub;          // buffers per (split, row): the tcgen05 epilogue uses one per column half
   uint64_t* cand;
@@ -115,6 +117,7 @@ struct ScanParams {
   float* dump;            // dense [b x n_items] score dump (bb_debug_scores) or nullptr
   unsigned long long* stat_candidates;
   int32_t* err_flag;      // set by watchdogs before trapping
+  uint32_t* wave_counter; // producers that finished issuing a unit's loads (keeps the CTA groups of a wave in step)
   int32_t debug_flags;    // perf triage (env BB_DEBUG_FLAGS): 1 = epilogue never inserts, 2 = epilogue skips TMEM loads
 };
 
@@ -169,7 +172,8 @@ static __device__ __noinline__ bool item_ok(const ScanParams& P, int row, int64_
   if (item >= P.n_items) return false;
   if (P.self_id != nullptr && __ldg(P.self_id + row) == static_cast<int32_t>(item + P.id_offset)) return false;
   if (P.cons == nullptr) return true;
-  const bb_constraint c = P.cons[static_cast<int64_t>(row) * P.cons_stride];
+  const int64_t ci = P.cons_index != nullptr ? __ldg(P.cons_index + row) : static_cast<int64_t>(row) * P.cons_stride;
+  const bb_constraint c = P.cons[ci];
   return constraint_ok(P, c, item);
 }
 
@@ -284,10 +288,11 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
 // buffer could overflow on the next group, publish its sorted prefix, and raise the
 // row's shared threshold (own k'-th best and the cross-stream refinement).
 // `force_mask`: lanes whose buffer is compacted regardless of fill (unit end: leave a sorted, published prefix).
+// `headroom`: appends a lane may make before the next call (the buffer must not overflow in between).
 __device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane,
-                                                      unsigned force_mask = 0u, bool refine = true) {
+                                                      unsigned force_mask = 0u, bool refine = true, int headroom = 32) {
   __syncwarp();
-  unsigned need = __ballot_sync(kFull, st.cnt > kCap - 32) | force_mask;
+  unsigned need = __ballot_sync(kFull, st.cnt > kCap - headroom) | force_mask;
   const int n_compactions = __popc(need);
   while (need) {
     const int src = __ffs(need) - 1;

@@ -258,11 +258,27 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_phase = 0;
       const uint32_t a_full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_a_full), 0) : smem_u32(bar_a_full);
-      for (int u = group; u < n_units; u += n_groups) {
+      int wave = 0;
+      for (int u = group; u < n_units; u += n_groups, ++wave) {
         const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
         int t0, t1;
         split_tile_range(P, split, t0, t1);
         const int row0 = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta;
+        // wave barrier: the query blocks that stream the same catalog split share it through L2 only while they
+        // stay in step; do not start wave w before every CTA issued all loads of wave w-1 (all CTAs are
+        // co-resident: the grid never exceeds one CTA per SM)
+        if (wave > 0 && P.wave_counter != nullptr && !(P.debug_flags & 4)) {
+          const uint32_t target = static_cast<uint32_t>(min(wave * n_groups, n_units)) * CG;
+          const long long t0w = clock64();
+          while (*reinterpret_cast<volatile uint32_t*>(P.wave_counter) < target) {
+            __nanosleep(200);
+            if (clock64() - t0w > kWatchdogCycles) {
+              if (err != nullptr) atomicExch(err, 107);
+              __threadfence_system();
+              __trap();
+            }
+          }
+        }
         // resident query operand: wait until the previous unit's MMAs stopped reading it
         mbar_wait(smem_u32(bar_a_empty), a_phase ^ 1, err, 101);
         a_phase ^= 1;
@@ -279,6 +295,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
         }
+        if (P.wave_counter != nullptr) atomicAdd(P.wave_counter, 1u);
       }
     }
     __syncwarp();
@@ -287,6 +304,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     if (leader) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_phase = 0;
       constexpr uint32_t idesc = make_idesc(128 * CG, kTcTile);
+      long long t_acc_wait = 0, t_full_wait = 0;     // pipeline triage: who makes the MMA issuer wait
+      const long long t_begin = clock64();
       for (int u = group; u < n_units; u += n_groups) {
         const int split = u / P.n_qblocks;
         int t0, t1;
@@ -294,11 +313,15 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         mbar_wait(smem_u32(bar_a_full), a_phase, err, 103);
         a_phase ^= 1;
         for (int t = t0; t < t1; ++t) {
+          long long tw = clock64();
           mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1, err, 104);
+          t_acc_wait += clock64() - tw;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kAccCols;
           for (int kb = 0; kb < n_kb; ++kb) {
+            tw = clock64();
             mbar_wait(smem_u32(bar_full + stage), phase, err, 105);
+            t_full_wait += clock64() - tw;
             tc_fence_after();
             if (lane == 0) {
               const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + kb * kAkbBytes));
@@ -322,6 +345,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (lane == 0) umma_commit<CG>(smem_u32(bar_a_empty));            // query operand no longer read
         __syncwarp();
       }
+      if (lane == 0 && P.stat_candidates != nullptr) {
+        atomicAdd(P.stat_candidates + 4, static_cast<unsigned long long>(t_acc_wait));
+        atomicAdd(P.stat_candidates + 5, static_cast<unsigned long long>(t_full_wait));
+        atomicAdd(P.stat_candidates + 6, static_cast<unsigned long long>(clock64() - t_begin));
+      }
     }
   } else if (warp >= 4) {
     // ============================== epilogue: mask + running-threshold top-k ==============================
@@ -332,7 +360,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t* theme_row = smem_theme + row_in_cta;  // this row's allowed-theme words at [w * 128]
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t acc_empty_leader_base = (CG == 2) ? mapa_u32(smem_u32(bar_acc_empty), 0) : smem_u32(bar_acc_empty);
-    const bool use_cons = P.cons != nullptr && P.shared_valid == nullptr;
+    const bool use_cons = P.cons != nullptr && P.class_valid == nullptr;   // per-row prefilter (no class bitmaps)
     unsigned stat_appends = 0, stat_slow = 0, stat_compact = 0;   // per-thread / per-warp counters (debug statistics)
     for (int u = group; u < n_units; u += n_groups) {
       const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
@@ -351,10 +379,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int64_t sl = static_cast<int64_t>(__ldg(P.self_id + q)) - P.id_offset;
         if (sl >= 0 && sl < P.n_items) self_local = sl;
       }
+      const uint32_t* class_row = nullptr;           // this row's constraint-set validity bitmap (class mode)
       if (q_valid && P.cons != nullptr) {
-        const bb_constraint c = P.cons[static_cast<int64_t>(q) * P.cons_stride];
-        needs_full = c.allow_bitmap >= 0 || c.excl_list[0] >= 0 || c.excl_list[1] >= 0 || c.excl_list[2] >= 0 ||
-                     (c.theme_set >= 0 && P.theme_words > 32);
+        const int64_t ci = P.cons_index != nullptr ? __ldg(P.cons_index + q) : static_cast<int64_t>(q) * P.cons_stride;
+        const bb_constraint c = P.cons[ci];
+        if (P.class_valid != nullptr) class_row = P.class_valid + ci * P.class_words;
+        needs_full = P.class_valid != nullptr ? false : c.allow_bitmap >= 0 || c.excl_list[0] >= 0 || c.excl_list[1] >= 0 || c.excl_list[2] >= 0 ||
+                     (c.theme_set >= 0 && P.theme_words > 32);   // (class bitmaps already include all of these)
         if ((c.flags & BB_C_ALWAYS_FALSE) || c.parts_max < c.parts_min || c.year_max < c.year_min) dead = true;
         pmin = c.parts_min;
         prange = static_cast<unsigned>(c.parts_max) - static_cast<unsigned>(c.parts_min);
@@ -373,6 +404,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const int64_t slot = (static_cast<int64_t>(split) * P.n_sub + half) * P.b_pad + q;
       st.buf = P.cand + slot * kCap;
       st.slot = slot;
+      int next_pub = 32;                             // early-publish schedule of a cold stream
       const bool share_thr = !dead && P.dump == nullptr;
       uint32_t thr_next = share_thr ? __ldcg(P.thr_g + q) : 0u;   // shared threshold, fetched one tile ahead
       for (int t = t0; t < t1; ++t) {
@@ -386,13 +418,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int64_t item0 = static_cast<int64_t>(t) * kTcTile;
 #pragma unroll 1
         for (int chunk = half * kChunksPerWarp; chunk < (half + 1) * kChunksPerWarp; ++chunk) {
-          if (P.debug_flags & 2) break;
+          if (P.debug_flags & 2) {                 // triage mode: never touch TMEM, just recycle the accumulator
+            if (chunk == (half + 1) * kChunksPerWarp - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(acc_empty_leader_base + acc * 8);
+                else mbar_arrive_local(acc_empty_leader_base + acc * 8);
+              }
+            }
+            continue;
+          }
           uint32_t r[32];
           tmem_ld32(taddr + chunk * 32, r);
           // this lane also "owns" one column of the chunk: fetch and unpack its metadata while the TMEM load is
           // in flight (only batches with per-row constraints pay for it)
           const int64_t col_item = item0 + chunk * 32 + lane;
           uint4 cm = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t class_word = 0xffffffffu;
+          if (class_row != nullptr) class_word = __ldg(class_row + ((item0 + chunk * 32) >> 5));
           if (use_cons) {
             int2 mt = make_int2(0, 0);
             if (col_item < P.n_items) mt = __ldg(P.meta + col_item);
@@ -403,6 +447,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             cm.w = (c_theme >= 0 && c_theme < 1024) ? (1u << (c_theme & 31)) : 0u;                  // theme bit (0 = NULL)
           }
           tmem_ld_wait();
+          if (chunk == (half + 1) * kChunksPerWarp - 1) {
+            // the tile's last slice is in registers: hand the accumulator back to the MMA issuer BEFORE
+            // processing it, so slow-path work and compactions overlap the next tile's MMAs
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(acc_empty_leader_base + acc * 8);
+              else mbar_arrive_local(acc_empty_leader_base + acc * 8);
+            }
+          }
           if (P.dump != nullptr) {
             if (q_valid) {
 #pragma unroll
@@ -423,9 +477,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= st.thr) ? (1u << j) : 0u;
             pm &= ~__ballot_sync(kFull, col_item >= P.n_items);
-            if (P.shared_valid != nullptr) {
-              // one constraint shared by the whole batch: its validity bitmap was built by the mask kernel
-              pm &= __ldg(P.shared_valid + ((item0 + chunk * 32) >> 5));
+            if (P.class_valid != nullptr) {
+              // few distinct constraint sets in the batch: their validity bitmaps were built by the mask kernel,
+              // one prefetched word masks this row's 32 columns
+              pm &= class_word;
             } else if (use_cons) {
               // column owners publish their item's unpacked metadata (prefetched above) in shared memory;
               // every row then checks only ITS OWN passing columns (trip count = max passes of one row)
@@ -469,16 +524,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                   }
                 }
               }
-              stat_compact += warp_compact_if_needed(P, st, q, lane);
             }
           }
         }
-        // accumulator drained: hand it back to the MMA issuer
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster(acc_empty_leader_base + acc * 8);
-          else mbar_arrive_local(acc_empty_leader_base + acc * 8);
+        // deferred compaction (after the accumulator was released): a tile appends at most 32 keys per chunk
+        if (P.dump == nullptr && !(P.debug_flags & 3)) {
+          // cold streams (no threshold yet) publish a small sorted prefix early: the row's concurrently cold
+          // streams then find a shared threshold after ~32 candidates each instead of ~200 each
+          const bool pub_now = !dead && st.thr == -INFINITY && st.cnt >= next_pub;
+          if (pub_now) next_pub *= 2;                // 32, 64, 128, then only the regular overflow trigger
+          const unsigned early = __ballot_sync(kFull, pub_now);
+          stat_compact += warp_compact_if_needed(P, st, q, lane, early, true, 32 * kChunksPerWarp);
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;

@@ -189,7 +189,8 @@ class ScoringEngine:
         return b[:n].astype(bool)
 
     # ------------------------------------------------------------------ the hot path
-    def _batch(self, a: _Args, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2):
+    def _batch(self, a: _Args, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2,
+               constraint_index=None):
         ref = next(x for x in (q_emb, q_item, q_cf) if x is not None)
         b = int(ref.shape[0])
         qb = L.bb_query_batch()
@@ -210,7 +211,7 @@ class ScoringEngine:
             # device-resident descriptors: uint8 tensor [n, 36] holding bb_constraint records
             if constraints.dtype != torch.uint8 or constraints.dim() != 2 or constraints.shape[1] != L.CONSTRAINT_DTYPE.itemsize:
                 raise TypeError("device constraints must be a uint8 tensor of shape [n, 36]")
-            if constraints.shape[0] not in (1, b):
+            if constraint_index is None and constraints.shape[0] not in (1, b):
                 raise ValueError("constraints must have 1 or n_queries entries")
             t = constraints.contiguous()
             a.keep.append(t)
@@ -219,23 +220,33 @@ class ScoringEngine:
             qb.n_constraints = int(t.shape[0])
         elif constraints is not None:
             c = np.ascontiguousarray(np.atleast_1d(constraints), dtype=L.CONSTRAINT_DTYPE)
-            if c.shape[0] not in (1, b):
+            if constraint_index is None and c.shape[0] not in (1, b):
                 raise ValueError("constraints must have 1 or n_queries entries")
             a.keep.append(c)
             qb.constraints = c.ctypes.data
             qb.n_constraints = c.shape[0]
+        qb.constraint_index = a.ptr(constraint_index, np.int32, (b,))
         qb.self_id = a.ptr(self_id, np.int32, (b,))
         qb.precision = L.PRECISIONS[precision]
         qb.flags = L.BB_Q_SCORES_AS_L2 if as_l2 else 0
         return qb, b
 
+    @staticmethod
+    def dedupe_constraints(constraints: np.ndarray):
+        """[B] descriptors -> (distinct [C], index int32 [B]) for the ``constraint_index`` form of ``search``."""
+        c = np.ascontiguousarray(np.atleast_1d(constraints), dtype=L.CONSTRAINT_DTYPE)
+        raw = c.view(np.uint8).reshape(c.shape[0], -1)
+        uniq, inv = np.unique(raw, axis=0, return_inverse=True)
+        return uniq.reshape(-1).view(L.CONSTRAINT_DTYPE).copy(), inv.astype(np.int32).reshape(-1)
+
     def search(self, k: int, q_emb=None, q_item=None, q_cf=None, w_content=1.0, w_cf=0.0, constraints=None,
-               self_id=None, precision: str = "fp32", as_l2: bool = False, out=None, stream=None
-               ) -> Tuple[object, object]:
+               self_id=None, precision: str = "fp32", as_l2: bool = False, out=None, stream=None,
+               constraint_index=None) -> Tuple[object, object]:
         """Fused score + blend + mask + top-k.  Returns (scores[B,k] float32, ids[B,k] int32).
         Outputs are CUDA tensors when any input is a CUDA tensor (or ``out`` is given), else NumPy."""
         a = _Args()
-        qb, b = self._batch(a, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2)
+        qb, b = self._batch(a, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2,
+                            constraint_index)
         if out is not None:
             scores, ids = out
             ps, pi = a.ptr(scores, np.float32, (b, k)), a.ptr(ids, np.int32, (b, k))

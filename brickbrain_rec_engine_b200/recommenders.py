@@ -468,10 +468,12 @@ class HybridRecommender:
                     ex[0] = li
                     d["excl_list"] = ex
             descs.append(d)
+        # queries that share a constraint set (popular filters) share one validity bitmap on the device
+        distinct, index = ScoringEngine.dedupe_constraints(np.stack(descs))
         return self.engine.search(top_k, q_item=q_item, q_cf=q_cf,
                                   w_content=self.content_weight if q_item is not None else 0.0,
                                   w_cf=self.collaborative_weight if q_cf is not None else 0.0,
-                                  constraints=np.stack(descs), self_id=self_id, precision=precision)
+                                  constraints=distinct, constraint_index=index, self_id=self_id, precision=precision)
 
 
 def accelerate(reference_hybrid, themes: Dict[int, str], owned=None, wishlisted=None, device: int = 0,

@@ -105,7 +105,11 @@ typedef struct bb_query_batch {
   const float* w_cf;                /* [B] per-query CF weight, or NULL -> w_cf_all */
   float w_content_all, w_cf_all;    /* reference default 0.4 / 0.6 (recommendation_system.py:609-610) */
   const bb_constraint* constraints; /* n_constraints entries, or NULL */
-  int32_t n_constraints;            /* 0, 1 (shared by all queries) or B */
+  int32_t n_constraints;            /* 0, 1 (shared by all queries), B (one per query), or C distinct sets when
+                                       constraint_index is given */
+  const int32_t* constraint_index;  /* [B] index of each query's entry in constraints[], or NULL.  Batches whose
+                                       queries share a few distinct constraint sets (<= 64) are masked through
+                                       per-set validity bitmaps built once per call by the mask kernel */
   const int32_t* self_id;           /* [B] global id excluded per query (-1 none), or NULL */
   int32_t precision;                /* BB_PREC_* */
   uint32_t flags;                   /* BB_Q_* */
@@ -122,6 +126,9 @@ typedef struct bb_info {
   int64_t last_appends;     /* candidates appended by the last scan's epilogue */
   int64_t last_slow_chunks; /* 32-column chunks that entered the epilogue slow path */
   int64_t last_compactions; /* candidate-buffer compactions (warp sorts) */
+  int64_t mma_wait_epilogue_cycles; /* sum over MMA issuers: cycles waiting for a free TMEM accumulator */
+  int64_t mma_wait_tma_cycles;      /* sum over MMA issuers: cycles waiting for operand stages */
+  int64_t mma_total_cycles;         /* sum over MMA issuers: cycles in the unit loop */
   double bytes_fp32, bytes_bf16; /* resident operand bytes */
   double scan_ms;           /* device time of the scan kernels since bb_set_profiling(h, 1) (CUDA events) */
   int64_t scan_launches;    /* scan kernel launches covered by scan_ms */

@@ -74,8 +74,10 @@ class FakeEngine:
     def _valid(self, d):
         return eval_descriptor(d, self.num_parts, self.year, self.theme, self.theme_sets, self.allow, self.excl, self.id_offset)
 
+    dedupe_constraints = staticmethod(lambda c: __import__("brickbrain_rec_engine_b200").ScoringEngine.dedupe_constraints(c))
+
     def search(self, k, q_emb=None, q_item=None, q_cf=None, w_content=1.0, w_cf=0.0, constraints=None, self_id=None,
-               precision="fp32", as_l2=False, out=None, stream=None):
+               precision="fp32", as_l2=False, out=None, stream=None, constraint_index=None):
         self.calls.append("search")
         ref = next(x for x in (q_emb, q_item, q_cf) if x is not None)
         b = ref.shape[0]
@@ -91,7 +93,8 @@ class FakeEngine:
         valid = None
         if constraints is not None:
             c = np.atleast_1d(constraints)
-            valid = np.stack([self._valid(c[j if c.shape[0] > 1 else 0]) for j in range(b)])
+            pick = (lambda j: int(constraint_index[j])) if constraint_index is not None else (lambda j: j if c.shape[0] > 1 else 0)
+            valid = np.stack([self._valid(c[pick(j)]) for j in range(b)])
         sid = None if self_id is None else np.asarray(self_id) - self.id_offset
         ids, sc = bo.fused_hybrid_topk(s, k, valid=valid, self_ids=sid)
         ids = np.where(ids >= 0, ids + self.id_offset, -1).astype(np.int32)

@@ -118,7 +118,7 @@ def test_fused_hybrid_topk_with_constraints(bb, precision):
     themes, emb, itf, parts, year, theme = _catalog(n, d, f, 21)
     q_items = np.arange(0, n, n // b)[:b].astype(np.int32)
     u = synth.cf_factors(b, f, 30)
-    rated = {j: np.sort(np.random.default_rng(100 + j).choice(n, 25, replace=False)).astype(np.int32) for j in range(8)}
+    rated = {j: np.sort(np.random.default_rng(100 + j).choice(n, 25, replace=False)).astype(np.int32) for j in range(6)}
     eng = bb.ScoringEngine(n, d, f)
     eng.load_catalog(emb=emb, item_factors=itf, num_parts=parts, year=year, theme_id=theme)
     descs, specs = _scenario_descs(bb, eng, themes, rated, b)
@@ -127,9 +127,15 @@ def test_fused_hybrid_topk_with_constraints(bb, precision):
     e_unit = bo.l2_normalize_rows(emb)
     ref = bo.fused_hybrid_scores(e_unit[q_items], u, e_unit, itf, np.full(b, 0.4, np.float32), np.full(b, 0.6, np.float32))
     valid = np.stack([bo.constraint_mask(s, parts, year, theme) for s in specs])
-    rid, rs = bo.fused_hybrid_topk(ref, k, valid=valid, self_ids=q_items, exclusions=[rated[j % 8] for j in range(b)])
+    rid, rs = bo.fused_hybrid_topk(ref, k, valid=valid, self_ids=q_items, exclusions=[rated[j % 6] for j in range(b)])
     assert_topk_equal(rid, rs, ids, scores, what=precision)
     assert eng.info()["launches"] > 0
+    # same batch through the deduplicated form (distinct constraint sets + per-query index -> class bitmaps)
+    distinct, index = eng.dedupe_constraints(descs)
+    assert distinct.shape[0] < b
+    s2, i2 = eng.search(k, q_item=q_items, q_cf=u, w_content=0.4, w_cf=0.6, constraints=distinct, constraint_index=index,
+                        self_id=q_items, precision=precision)
+    assert np.array_equal(i2, ids) and np.array_equal(s2, scores)
     eng.close()
 
 

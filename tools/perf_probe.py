@@ -27,30 +27,35 @@ def child(n, b, k, cons):
     q = torch.nn.functional.normalize(torch.randn(b, d, device=dev, generator=g) + 0.9, dim=1)
     u = torch.randn(b, f, device=dev, generator=g) / 8
     c = None
+    cidx = None
     if cons == 1:
         cn = bb.no_constraint()
         cn["parts_min"], cn["parts_max"] = 1, 1000
         c = torch.from_numpy(np.atleast_1d(cn).view(np.uint8).reshape(1, -1).copy()).to(dev)
-    elif cons == 2:
+    elif cons in (2, 3):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import bench
         descs, bitmaps, _ = bench.scenario_descriptors(b)
         eng.set_theme_sets(bitmaps)
-        c = torch.from_numpy(descs.view(np.uint8).reshape(b, -1).copy()).to(dev)
+        if cons == 3:
+            descs, cidx_np = eng.dedupe_constraints(descs)
+            cidx = torch.from_numpy(cidx_np).to(dev)
+        c = torch.from_numpy(descs.view(np.uint8).reshape(descs.shape[0], -1).copy()).to(dev)
     for prec in ("bf16",):
         for _ in range(2):
-            eng.search(k, q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6, constraints=c, precision=prec)
+            eng.search(k, q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6, constraints=c, constraint_index=cidx, precision=prec)
         torch.cuda.synchronize()
         eng.set_profiling(True)
         for _ in range(3):
-            eng.search(k, q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6, constraints=c, precision=prec)
+            eng.search(k, q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6, constraints=c, constraint_index=cidx, precision=prec)
         torch.cuda.synchronize()
         i = eng.info()
         ms = i["scan_ms"] / i["scan_launches"]
         tf = 2.0 * b * n * 448 / (ms * 1e-3) / 1e12
         print(f"flags={os.environ.get('BB_DEBUG_FLAGS','0')} cg={i['cta_group']} cons={cons} n={n} b={b} k={k}: scan {ms:.2f} ms = {tf:.1f} TFLOP/s "
               f"units={i['last_units']} cands={i['last_candidates']} appends={i['last_appends']} slow_chunks={i['last_slow_chunks']} "
-              f"compactions={i['last_compactions']}", flush=True)
+              f"compactions={i['last_compactions']} mma_wait_epi={i['mma_wait_epilogue_cycles']/max(1,i['mma_total_cycles']):.3f} "
+              f"mma_wait_tma={i['mma_wait_tma_cycles']/max(1,i['mma_total_cycles']):.3f}", flush=True)
 
 
 if __name__ == "__main__":
@@ -61,7 +66,7 @@ if __name__ == "__main__":
     for n in sizes:
         for cg in ("2",):
             for flags in ("0", "1"):
-                for cons in (0, 1, 2):
+                for cons in (0, 1, 2, 3):
                     if flags != "0" and cons:
                         continue
                     env = dict(os.environ, BB_DEBUG_FLAGS=flags, BB_CTA_GROUP=cg)
