@@ -211,16 +211,32 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   p.n_tiles = static_cast<int>((h->cfg.n_items + p.tile_items - 1) / p.tile_items);
   if (p.n_tiles < 1) p.n_tiles = 1;
   const int hw_groups = tc ? h->sm_count / h->cta_group : h->sm_count * 2;
-  const long long total = static_cast<long long>(p.n_qblocks) * p.n_tiles;
-  long long waves = total / (static_cast<long long>(hw_groups) * 8);
-  if (waves < 1) waves = 1;
-  if (waves > 16) waves = 16;
-  long long splits = (hw_groups * waves + p.n_qblocks - 1) / p.n_qblocks;
-  if (splits > p.n_tiles) splits = p.n_tiles;
-  if (splits < 1) splits = 1;
-  // bound candidate memory (2 KB per (split, row)) to 2 GiB
-  const long long max_splits = (2ll << 30) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? kTcSubStreams : 1));
-  if (splits > max_splits) splits = max_splits > 0 ? max_splits : 1;
+  // Catalog splits.  Every unit pays a fixed price (cold candidate streams, a sorted + published prefix at its end),
+  // so units should be long (>= ~512 tiles) but there must be enough of them to fill the machine evenly: pick the
+  // smallest split count within reach whose static round-robin schedule keeps >= 97% of the CTA groups busy.
+  const long long mem_cap = (5ll << 29) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? kTcSubStreams : 1));   // 2.5 GiB
+  long long s_cap = p.n_tiles;
+  if (s_cap > 64) s_cap = 64;
+  if (s_cap > mem_cap) s_cap = mem_cap > 0 ? mem_cap : 1;
+  long long s_lo = p.n_tiles / 512;
+  const long long s_fill = (hw_groups + p.n_qblocks - 1) / p.n_qblocks;    // enough units to occupy every group once
+  if (s_lo < s_fill) s_lo = s_fill;
+  if (s_lo < 1) s_lo = 1;
+  if (s_lo > s_cap) s_lo = s_cap;
+  long long splits = s_lo;
+  double best = -1.0;
+  const long long w_lo = (s_lo - 8 > s_fill) ? s_lo - 8 : (s_fill < s_lo ? s_fill : s_lo);
+  for (long long sc = w_lo; sc <= s_cap && sc <= s_lo + 16; ++sc) {
+    const long long units = sc * p.n_qblocks;
+    const long long rounds = (units + hw_groups - 1) / hw_groups;
+    // occupancy of the static schedule, with a mild preference for the target unit length
+    const double eff = static_cast<double>(units) / static_cast<double>(rounds * hw_groups) -
+                       0.001 * static_cast<double>(sc > s_lo ? sc - s_lo : s_lo - sc);
+    if (eff > best + 1e-9) {
+      best = eff;
+      splits = sc;
+    }
+  }
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
   p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
