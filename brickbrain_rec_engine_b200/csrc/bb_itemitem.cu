@@ -2,7 +2,9 @@
 // the schema stub is src/db/user_interaction_schema.sql:136-145): cosine between
 // item columns of the sparse user x item rating matrix, top-k neighbours per item.
 //
-// The N x N Gram matrix is never materialized.  Pipeline:
+// Two paths.  Catalog-sized item sets (N*N*4 B <= 6 GiB, e.g. the reference's 25,216 sets = 2.5 GB) take the
+// dense-Gram path below (global fire-and-forget reductions + one streaming select pass).  Larger item sets take
+// the accumulator path, where the N x N Gram matrix is never materialized:
 //   1. CSR -> CSC on device (histogram, scan, scatter) + column square norms,
 //   2. items ordered by descending degree bucket (hot columns first: LPT balance),
 //   3. one CTA per item i: a shared-memory accumulator over all items j receives
@@ -220,12 +222,104 @@ ii_main_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ i
   }
 }
 
+// ---------------------------------------------------------------- dense-Gram path (catalog-sized item sets)
+// For N items with N*N*4 B within budget the Gram matrix G = X^T X is accumulated in HBM with fire-and-forget
+// global reductions (RED.ADD.F32: ~1 per lane per cycle per SM, no serialization behind hot items), one warp per
+// user: every ordered pair (a, b) of the user's rated items adds r_a * r_b to G[a][b].  A second kernel streams
+// each row once (coalesced), normalizes by the diagonal and selects the top-k.  Integer ratings keep every partial
+// sum exact (< 2^24), so the result does not depend on the order of the atomics.
+__global__ void __launch_bounds__(256)
+ii_gram_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+               int64_t n_users, int n_items, float* __restrict__ gram) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t u = warp0; u < n_users; u += n_warps) {
+    const int64_t lo = indptr[u], hi = indptr[u + 1];
+    const int d = static_cast<int>(hi - lo);
+    // pairs (a, b): lanes sweep the flattened d*d index space
+    for (int p = lane; p < d * d; p += 32) {
+      const int a = p / d, b = p - a * d;
+      const int32_t ia = __ldg(indices + lo + a), ib = __ldg(indices + lo + b);
+      atomicAdd(gram + static_cast<int64_t>(ia) * n_items + ib, __ldg(values + lo + a) * __ldg(values + lo + b));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kIIThreads)
+ii_select_kernel(const float* __restrict__ gram, int n_items, int k, float* __restrict__ out_scores,
+                 int32_t* __restrict__ out_ids) {
+  __shared__ uint64_t stages[kIIWarps * kCap];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+    const float* row = gram + static_cast<int64_t>(i) * n_items;
+    const float sq_i = row[i];
+    IIMerger mg;
+    mg.init(stages + warp * kCap, lane);
+    for (int base = warp * 32; base < n_items; base += kIIThreads) {
+      const int j = base + lane;
+      uint64_t key = 0ull;
+      if (j < n_items) {
+        const float g = __ldg(row + j);
+        if (g > 0.f && j != i) key = make_key(g / (sqrtf(sq_i) * sqrtf(__ldg(gram + static_cast<int64_t>(j) * n_items + j))), static_cast<uint32_t>(j));
+      }
+      mg.offer(key);
+    }
+    mg.flush();
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t* s0 = stages;
+      uint64_t mine[kEpl / 2];
+#pragma unroll
+      for (int x = 0; x < kEpl / 2; ++x) mine[x] = s0[(x << 5) | lane];
+      __syncwarp();
+      IIMerger fin;
+      fin.init(s0, lane);
+#pragma unroll
+      for (int x = 0; x < kEpl / 2; ++x) fin.offer(mine[x]);
+      for (int w = 1; w < kIIWarps; ++w)
+        for (int x = 0; x < kCap / 2; x += 32) fin.offer(stages[w * kCap + x + lane]);
+      fin.flush();
+      int n_pos = 0;
+      for (int x = 0; x < k; x += 32) {
+        const uint64_t key = (x + lane < k) ? s0[x + lane] : 0ull;
+        n_pos += __popc(__ballot_sync(kFull, key != 0ull));
+        if (x + lane < k && key != 0ull) {
+          out_scores[static_cast<int64_t>(i) * k + x + lane] = key_score(key);
+          out_ids[static_cast<int64_t>(i) * k + x + lane] = key_id(key);
+        }
+      }
+      if (n_pos < k && lane == 0) {          // fewer than k co-rated neighbours: zero-similarity items by ascending id
+        int filled = n_pos;
+        for (int j = 0; j < n_items && filled < k; ++j) {
+          if (j == i) continue;
+          bool used = false;
+          for (int x = 0; x < n_pos; ++x) used |= (key_id(s0[x]) == j);
+          if (used) continue;
+          out_scores[static_cast<int64_t>(i) * k + filled] = 0.f;
+          out_ids[static_cast<int64_t>(i) * k + filled] = j;
+          ++filled;
+        }
+        for (; filled < k; ++filled) {
+          out_scores[static_cast<int64_t>(i) * k + filled] = -INFINITY;
+          out_ids[static_cast<int64_t>(i) * k + filled] = -1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr size_t kGramBudgetBytes = static_cast<size_t>(6) << 30;    // dense path when N*N*4 B <= 6 GiB (N <= ~40k)
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
 size_t item_item_workspace_bytes(int64_t n_users, int n_items, int64_t nnz) {
   (void)n_users;
+  const size_t gram = static_cast<size_t>(n_items) * n_items * sizeof(float);
+  if (gram <= kGramBudgetBytes) return align_up(gram, 256) + 256;
   size_t b = 0;
   b += align_up(static_cast<size_t>(n_items + 1) * 8, 256);   // col_cnt
   b += align_up(static_cast<size_t>(n_items + 1) * 8, 256);   // col_ptr
@@ -249,6 +343,19 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) return e;
   if (item_item_workspace_bytes(n_users, n_items, nnz) > workspace_bytes) return cudaErrorInvalidValue;
+  int dev0 = 0, sms0 = 148;
+  cudaGetDevice(&dev0);
+  cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+  const size_t gram_bytes = static_cast<size_t>(n_items) * n_items * sizeof(float);
+  if (gram_bytes <= kGramBudgetBytes) {
+    float* gram = static_cast<float*>(workspace);
+    e = cudaMemsetAsync(gram, 0, gram_bytes, stream);
+    if (e != cudaSuccess) return e;
+    ii_gram_kernel<<<sms0 * 8, 256, 0, stream>>>(indptr, indices, values, n_users, n_items, gram);
+    ii_select_kernel<<<sms0 * 4, kIIThreads, 0, stream>>>(gram, n_items, k, out_scores, out_ids);
+    if (n_launches != nullptr) *n_launches = 2;
+    return cudaGetLastError();
+  }
 
   unsigned char* w = static_cast<unsigned char*>(workspace);
   auto take = [&](size_t bytes) { unsigned char* p = w; w += align_up(bytes, 256); return p; };
