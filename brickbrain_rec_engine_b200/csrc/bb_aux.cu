@@ -194,25 +194,47 @@ __global__ void __launch_bounds__(128)
 merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restrict__ q_f32,
                   const float* __restrict__ cat_f32, int as_l2, float* __restrict__ out_scores,
                   int32_t* __restrict__ out_ids) {
-  __shared__ uint64_t stage[kCap];
+  __shared__ uint64_t stage_all[4][kCap];
+  uint64_t* stage = stage_all[0];
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  if (warp == 0) {
+  // Phase 1: the four warps gather disjoint quarters of the row's streams (counts are fetched lane-parallel so
+  // the walk is not a chain of dependent L2 round trips), then warp 0 merges the four partial tops.
+  {
     WarpMerger mg;
-    mg.init(stage, lane);
+    mg.init(stage_all[warp], lane);
     const uint32_t thr = __ldcg(P.thr_g + q);
-    for (int s = 0; s < P.n_splits * P.n_sub; ++s) {
-      const int64_t slot = static_cast<int64_t>(s) * P.b_pad + q;
-      const int cnt = __ldcg(P.cand_cnt + slot);
-      const uint64_t* buf = P.cand + slot * kCap;
-      for (int base = 0; base < cnt; base += 32) {
-        uint64_t key = (base + lane < cnt) ? __ldcg(buf + base + lane) : 0ull;
-        if (static_cast<uint32_t>(key >> 32) < thr) key = 0ull;
-        mg.offer(key);
+    const int n_slots = P.n_splits * P.n_sub;
+    for (int s0 = warp * 32; s0 < n_slots; s0 += 128) {
+      const int my_s = s0 + lane;
+      const int my_cnt = my_s < n_slots ? __ldcg(P.cand_cnt + static_cast<int64_t>(my_s) * P.b_pad + q) : 0;
+      for (int j = 0; j < 32 && s0 + j < n_slots; ++j) {
+        const int cnt = __shfl_sync(kFull, my_cnt, j);
+        if (cnt == 0) continue;
+        const uint64_t* buf = P.cand + (static_cast<int64_t>(s0 + j) * P.b_pad + q) * kCap;
+        for (int base = 0; base < cnt; base += 32) {
+          uint64_t key = (base + lane < cnt) ? __ldcg(buf + base + lane) : 0ull;
+          if (static_cast<uint32_t>(key >> 32) < thr) key = 0ull;
+          mg.offer(key);
+        }
       }
     }
     mg.flush();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t mine[kEpl / 2];
+#pragma unroll
+    for (int x = 0; x < kEpl / 2; ++x) mine[x] = stage[(x << 5) | lane];
+    __syncwarp();
+    WarpMerger fin;
+    fin.init(stage, lane);
+#pragma unroll
+    for (int x = 0; x < kEpl / 2; ++x) fin.offer(mine[x]);
+    for (int w = 1; w < 4; ++w)
+      for (int x = 0; x < kCap / 2; x += 32) fin.offer(stage_all[w][x + lane]);
+    fin.flush();
   }
   __syncthreads();
 

@@ -79,22 +79,35 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   // fence every outstanding global candidate store of the warp (ERRBAR) once per tile
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+template <bool kHint = false>
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
+  if constexpr (kHint) {
+    // suspend-time hint (ns): the (many) epilogue warps sleep in hardware instead of burning issue slots and power
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
   return ok;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+template <bool kHint = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int32_t* err_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait<kHint>(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait<kHint>(bar, parity)) {
     if (clock64() - t0 > kWatchdogCycles) {
       if (err_flag != nullptr) atomicExch(err_flag, code);
       __threadfence_system();
@@ -412,7 +425,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           st.thr = fmaxf(st.thr, ord2f(thr_next));
           thr_next = __ldcg(P.thr_g + q);
         }
-        mbar_wait(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
+        mbar_wait<true>(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols;
         const int64_t item0 = static_cast<int64_t>(t) * kTcTile;
