@@ -239,21 +239,31 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
   __syncthreads();
 
   if (rescore) {
-    // exact fp32 dot of the query operand with each surviving catalog row
+    // exact fp32 dot of the query operand with each surviving catalog row.  Eight lanes per candidate, four
+    // candidates per warp at a time: every lane keeps up to 14 independent 16-byte gathers in flight, which is what
+    // hides the latency of these scattered row reads.
     const float4* qv = reinterpret_cast<const float4*>(q_f32 + static_cast<int64_t>(q) * P.k_pad);
     const int n4 = P.k_pad >> 2;
-    for (int c = warp; c < kMaxSel; c += 4) {
+    const int sub = lane >> 3, l8 = lane & 7;
+    for (int c0 = warp * 4; c0 < kMaxSel; c0 += 16) {
+      const int c = c0 + sub;
       const uint64_t key = stage[c];
-      if (key == 0ull) continue;                       // warp-uniform
-      const int32_t gid = key_id(key);
-      const float4* ev = reinterpret_cast<const float4*>(cat_f32 + (static_cast<int64_t>(gid) - P.id_offset) * P.k_pad);
       float acc = 0.f;
-      for (int i = lane; i < n4; i += 32) {
-        const float4 a = __ldg(qv + i), b = __ldg(ev + i);
-        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      int32_t gid = -1;
+      if (key != 0ull) {
+        gid = key_id(key);
+        const float4* ev = reinterpret_cast<const float4*>(cat_f32 + (static_cast<int64_t>(gid) - P.id_offset) * P.k_pad);
+#pragma unroll 4
+        for (int i = l8; i < n4; i += 8) {
+          const float4 a = __ldg(qv + i), b = __ldg(ev + i);
+          acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+        }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) stage[c] = make_key(acc, static_cast<uint32_t>(gid));
+      acc += __shfl_xor_sync(kFull, acc, 4);
+      acc += __shfl_xor_sync(kFull, acc, 2);
+      acc += __shfl_xor_sync(kFull, acc, 1);
+      __syncwarp();
+      if (l8 == 0 && key != 0ull) stage[c] = make_key(acc, static_cast<uint32_t>(gid));
     }
     __syncthreads();
     if (warp == 0) {

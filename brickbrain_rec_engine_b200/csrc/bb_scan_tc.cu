@@ -36,6 +36,7 @@ constexpr int kTmemCols = 512;              // two accumulators
 constexpr int kEpiWarps = 4 * kTcSubStreams; // kTcSubStreams warps per TMEM lane quarter, each scans a column slice of every tile
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerWarp = (kAccCols / 32) / (kEpiWarps / 4);
+static_assert(kCap - 32 * kChunksPerWarp >= kMaxSel + 32, "candidate buffer too small for this many chunks per epilogue warp");
 constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata of the 32 columns of a chunk
 constexpr int kThemeBytes = 32 * 128 * 4;         // per-row allowed-theme bitmaps, word-major [32 words][128 rows]
 constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
@@ -555,7 +556,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (P.dump == nullptr) {
         // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units
         // that scan this row later start from everything this stream has learnt
-        const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt > 0);
+        // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
+        const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt >= 8);
         // (one of the row's column-slice streams refines; the others only sort + publish)
         stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, half == 0);
         P.cand_cnt[slot] = st.cnt;
