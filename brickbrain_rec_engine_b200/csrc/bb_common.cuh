@@ -79,6 +79,36 @@ __device__ __forceinline__ void warp_sort_desc(K (&v)[EPL], int lane) {
   }
 }
 
+// Final phase of the bitonic network: turns a BITONIC sequence of 32*EPL keys into a descending one.
+template <int EPL, typename K = uint64_t>
+__device__ __forceinline__ void warp_bitonic_merge_desc(K (&v)[EPL], int lane) {
+#pragma unroll
+  for (int j = 16 * EPL; j > 0; j >>= 1) {
+    if (j >= 32) {
+      const int ji = j >> 5;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int ip = i ^ ji;
+        if (ip > i) {
+          const K a = v[i], b = v[ip];
+          const bool sw = a < b;
+          v[i] = sw ? b : a;
+          v[ip] = sw ? a : b;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const K a = v[i];
+        const K b = __shfl_xor_sync(kFull, a, j);
+        const bool lower = (lane & j) == 0;
+        const K mx = a > b ? a : b, mn = a > b ? b : a;
+        v[i] = lower ? mx : mn;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- scan parameters
 struct ScanParams {
   // catalog shard
@@ -187,6 +217,7 @@ struct RowState {
   int cnt;
   uint64_t* buf;
   int64_t slot;           // (split * n_sub + sub) * b_pad + row
+  int sorted;             // keys at the front of buf that are already in descending order (from the last compaction)
 };
 
 __device__ __forceinline__ int32_t ld_acquire_s32(const int32_t* p) {
@@ -219,9 +250,46 @@ __device__ __forceinline__ uint64_t warp_compact_n(uint64_t* buf, int cnt, int k
   return __shfl_sync(kFull, kth, 31);
 }
 
-__device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, int lane, float* new_thr) {
+// Tail sort + merge: the first kMaxSel keys are already sorted (previous compaction), only the <= 128 newly
+// appended keys need sorting; one compare against the reversed tail yields the best kMaxSel of the union as a
+// bitonic sequence, one merge phase orders them.  ~3-4x fewer compare-exchanges than re-sorting all 256 keys.
+template <int TE>
+__device__ __forceinline__ uint64_t warp_compact_merge(uint64_t* buf, int cnt, int lane) {
+  constexpr int PE = kMaxSel / 32;
+  uint64_t p[PE], t[PE];
+#pragma unroll
+  for (int i = 0; i < PE; ++i) p[i] = __ldcg(buf + ((i << 5) | lane));
+  {
+    uint64_t tt[TE];
+#pragma unroll
+    for (int i = 0; i < TE; ++i) {
+      const int e = kMaxSel + ((i << 5) | lane);
+      tt[i] = (e < cnt) ? __ldcg(buf + e) : 0ull;
+    }
+    warp_sort_desc<TE>(tt, lane);
+#pragma unroll
+    for (int i = 0; i < PE; ++i) t[i] = (i < TE) ? tt[i < TE ? i : 0] : 0ull;
+  }
+  // c[e] = max(p[e], t[L-1-e]): element L-1-e lives in register PE-1-i of lane 31-lane
+#pragma unroll
+  for (int i = 0; i < PE; ++i) {
+    const uint64_t r = __shfl_sync(kFull, t[PE - 1 - i], 31 - lane);
+    p[i] = p[i] > r ? p[i] : r;
+  }
+  warp_bitonic_merge_desc<PE>(p, lane);
+#pragma unroll
+  for (int i = 0; i < PE; ++i) __stcg(buf + ((i << 5) | lane), p[i]);
+  return __shfl_sync(kFull, p[PE - 1], 31);
+}
+
+__device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, int sorted, int lane, float* new_thr) {
   uint64_t kth;
-  if (cnt <= 32) kth = warp_compact_n<1>(buf, cnt, k_sel, lane);
+  if (k_sel == kMaxSel && sorted == kMaxSel && cnt > kMaxSel) {
+    const int tail = cnt - kMaxSel;
+    if (tail <= 32) kth = warp_compact_merge<1>(buf, cnt, lane);
+    else if (tail <= 64) kth = warp_compact_merge<2>(buf, cnt, lane);
+    else kth = warp_compact_merge<4>(buf, cnt, lane);
+  } else if (cnt <= 32) kth = warp_compact_n<1>(buf, cnt, k_sel, lane);
   else if (cnt <= 64) kth = warp_compact_n<2>(buf, cnt, k_sel, lane);
   else if (cnt <= 128) kth = warp_compact_n<4>(buf, cnt, k_sel, lane);
   else kth = warp_compact_n<kEpl>(buf, cnt, k_sel, lane);
@@ -233,7 +301,7 @@ __device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, i
 // Cross-stream threshold refinement.  A query row is scanned by many independent streams (catalog splits x
 // column halves), each keeping its own sorted top-k' prefix.  If `need` streams each hold at least r keys
 // >= T then at least need*r >= k' valid items score >= T, so T is a valid lower bound of the row's k'-th best.
-// With n published streams the useful levels are the smallest r = 2^l with ceil(k'/r) <= n and the next two;
+// With n published streams the useful levels are the smallest r = 2^l with ceil(k'/r) <= n and the next one;
 // T_r = the ceil(k'/r)-th largest of the streams' r-th best keys and the bound is max_r T_r (r = k' is each
 // stream's own threshold).  This lets ~74 streams per row share a threshold close to the global one instead of
 // the max of their local ones.
@@ -264,7 +332,7 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
   while (r0 < P.k_sel && (P.k_sel + r0 - 1) / r0 > n_pub) r0 <<= 1;
   uint32_t best = 0u;
 #pragma unroll 1
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < 2; ++l) {
     const int r = r0 << l;
     if (r >= P.k_sel) break;                        // the r = k' level is the stream's own threshold
     const int need = (P.k_sel + r - 1) / r;
@@ -299,15 +367,17 @@ __device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowSt
     need &= need - 1;
     uint64_t* b = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(st.buf), src));
     const int c = __shfl_sync(kFull, st.cnt, src);
+    const int c_sorted = __shfl_sync(kFull, st.sorted, src);
     const int src_row = __shfl_sync(kFull, row, src);
     const long long src_slot = __shfl_sync(kFull, static_cast<long long>(st.slot), src);
     float nt;
-    const int nc = warp_compact(b, c, P.k_sel, lane, &nt);
+    const int nc = warp_compact(b, c, P.k_sel, c_sorted, lane, &nt);
     __threadfence();                                // sorted keys are visible before the count that advertises them
     if (lane == 0) atomicMax(P.pub_cnt + src_slot, nc);
     const uint32_t refined = refine ? warp_refine_threshold(P, src_row, lane) : 0u;
     if (lane == src) {
       st.cnt = nc;
+      st.sorted = nc;
       uint32_t o = f2ord(nt);
       o = refined > o ? refined : o;
       if (o > f2ord(st.thr)) {

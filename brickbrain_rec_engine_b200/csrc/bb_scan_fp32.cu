@@ -61,6 +61,7 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
   RowState st;
   st.thr = (warp < 4 && own_row < P.n_queries) ? -INFINITY : INFINITY;
   st.cnt = 0;
+  st.sorted = 0;
   st.slot = static_cast<int64_t>(split) * P.n_sub * P.b_pad + (warp < 4 ? own_row : 0);
   st.buf = P.cand + st.slot * kCap;
 

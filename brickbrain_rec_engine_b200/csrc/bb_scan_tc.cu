@@ -415,6 +415,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       RowState st;
       st.thr = dead ? INFINITY : -INFINITY;
       st.cnt = 0;
+      st.sorted = 0;
       const int64_t slot = (static_cast<int64_t>(split) * P.n_sub + half) * P.b_pad + q;
       st.buf = P.cand + slot * kCap;
       st.slot = slot;
