@@ -372,3 +372,97 @@ def test_large_catalog_properties(bb):
     recall = np.mean([len(set(a.tolist()) & set(t.tolist())) / k for a, t in zip(ids64.cpu(), top.indices.cpu())])
     assert recall >= 0.999, recall
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# more shapes, the reference's own feature shape, bulk / sharded drivers, re-entrancy
+# ---------------------------------------------------------------------------------------------
+def test_golden_content_f64_features(bb, golden_dir):
+    """The reference's own content matrix is ~10 float64 columns (recommendation_system.py:179-191); the engine
+    computes in fp32, so scores agree to 1e-5 relative and ids wherever the reference's gap exceeds that."""
+    g = _golden(golden_dir, "content_f64_golden.npz")
+    feat = g["feat"]
+    n = feat.shape[0]
+    themes = synth.themes_table()
+    cat = bb.CatalogTable(synth.set_nums(n), [f"Set {i}" for i in range(n)], np.full(n, 2020), np.full(n, 100),
+                          np.ones(n), ["x"] * n)
+    hyb = bb.HybridRecommender.from_arrays(cat, feat, themes)
+    k = int(g["k"])
+    for j, t in enumerate(g["targets"]):
+        ids, sc = _recs_arrays(hyb.content_recommender.get_similar_sets(cat.set_nums[int(t)], k), cat, k)
+        assert_topk_equal(g["ids"][j][None], g["scores"][j][None], ids, sc, what=f"f64 features, target {t}")
+    hyb.engine.close()
+
+
+@pytest.mark.parametrize("n,d,f,b,k", [(5, 3, 0, 2, 4), (300, 10, 5, 257, 128), (70000, 64, 0, 1, 100), (1000, 0, 16, 33, 10)])
+def test_odd_shapes_all_precisions(bb, n, d, f, b, k):
+    rng = np.random.default_rng(n + d + f)
+    emb = rng.standard_normal((n, d)).astype(np.float32) if d else None
+    itf = rng.standard_normal((n, f)).astype(np.float32) if f else None
+    q = rng.standard_normal((b, d)).astype(np.float32) if d else None
+    u = rng.standard_normal((b, f)).astype(np.float32) if f else None
+    eng = bb.ScoringEngine(n, d, f)
+    eng.load_catalog(emb=emb, item_factors=itf)
+    wc, wf = (0.4 if d else 0.0), (0.6 if f else 0.0)
+    ref = bo.fused_hybrid_scores(q, u, bo.l2_normalize_rows(emb) if d else None, itf,
+                                 np.full(b, wc, np.float32), np.full(b, wf, np.float32))
+    kk = min(k, 128)
+    rid, rs = bo.fused_hybrid_topk(ref, kk)
+    s, i = eng.search(kk, q_emb=q, q_cf=u, w_content=wc, w_cf=wf, precision="fp32")
+    assert_topk_equal(rid, rs, i, s, what=f"fp32 n={n} d={d} f={f}")
+    # bf16 scan + exact re-score: the candidate set comes from bf16 scores (k' = min(128, 1.25k+8) over-fetch), so on
+    # a dense ranking (k close to n) a few boundary items may differ; every returned score is exact fp32
+    s, i = eng.search(kk, q_emb=q, q_cf=u, w_content=wc, w_cf=wf, precision="bf16_rescore")
+    recall = np.mean([len(set(i[r][i[r] >= 0]) & set(rid[r][rid[r] >= 0])) / max(1, (rid[r] >= 0).sum()) for r in range(b)])
+    assert recall >= (0.999 if kk <= 100 and n >= 1000 else 0.97), recall
+    for r in range(b):
+        m = i[r] >= 0
+        np.testing.assert_allclose(s[r][m], ref[r][i[r][m]], rtol=RTOL, atol=2e-6)
+        assert (np.diff(s[r][m]) <= 0).all()
+    eng.close()
+
+
+def test_bulk_and_sharded_single_rank(bb):
+    import torch
+    n, d, f, users, k = 20000, 64, 16, 700, 20
+    emb = synth.embeddings(n, d, 1, "aniso")
+    itf = synth.cf_factors(n, f, 2)
+    uf = synth.cf_factors(users, f, 3)
+    liked = np.random.default_rng(4).integers(0, n, users).astype(np.int32)
+    eng = bb.ScoringEngine(n, d, f)
+    eng.load_catalog(emb=emb, item_factors=itf)
+    outs = bb.bulk_recommend(eng, uf, liked, k, batch=256, precision="bf16_rescore")
+    ids = np.concatenate([np.asarray(i) for _, i in outs])
+    e_unit = bo.l2_normalize_rows(emb)
+    ref = bo.fused_hybrid_scores(e_unit[liked], uf, e_unit, itf, np.full(users, 0.4, np.float32), np.full(users, 0.6, np.float32))
+    rid, _ = bo.fused_hybrid_topk(ref, k, self_ids=liked)
+    assert (ids == rid).mean() > 0.999
+    # device-resident inputs give device-resident outputs
+    outs_d = bb.bulk_recommend(eng, torch.from_numpy(uf).cuda(), torch.from_numpy(liked).cuda(), k, batch=512)
+    assert outs_d[0][1].is_cuda and np.array_equal(torch.cat([i for _, i in outs_d]).cpu().numpy(), ids)
+    eng.close()
+
+
+def test_reentrant_two_streams(bb):
+    """bb_search is re-entrant on an immutable catalog: two host threads on two CUDA streams."""
+    import threading
+    import torch
+    n, d, b, k = 30000, 128, 300, 32
+    emb = synth.embeddings(n, d, 1, "aniso")
+    eng = bb.ScoringEngine(n, d, 0)
+    eng.load_catalog(emb=emb)
+    qs = [synth.embeddings(b, d, 10 + t, "aniso") for t in range(2)]
+    want = [eng.search(k, q_emb=q, precision="bf16_rescore") for q in qs]
+    got = [None, None]
+
+    def work(t):
+        st = torch.cuda.Stream()
+        for _ in range(5):
+            got[t] = eng.search(k, q_emb=qs[t], precision="bf16_rescore", stream=st.cuda_stream)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for t in range(2):
+        assert np.array_equal(got[t][1], want[t][1]) and np.array_equal(got[t][0], want[t][0])
+    eng.close()
