@@ -58,6 +58,12 @@ struct Workspace {
   const void* tmap_q_ptr = nullptr;
   int tmap_q_rows = 0;
   int32_t* host_flag = nullptr;   // pinned
+  // per-stream control block on the device (concurrent searches on other streams must not share these):
+  // bytes [0,64) statistics, [64,68) wave-barrier counter, [128,132) error / watchdog flag
+  unsigned char* ctl = nullptr;
+  unsigned long long* stats() const { return reinterpret_cast<unsigned long long*>(ctl); }
+  uint32_t* wave_counter() const { return reinterpret_cast<uint32_t*>(ctl + 64); }
+  int32_t* err_flag() const { return reinterpret_cast<int32_t*>(ctl + 128); }
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -92,8 +98,7 @@ struct bb_handle {
   std::map<cudaStream_t, Workspace*> ws;
   std::atomic<long long> launches{0};
   std::atomic<long long> last_units{0};
-  unsigned long long* stat_dev = nullptr;
-  int32_t* err_dev = nullptr;
+  Workspace* last_ws = nullptr;   // most recently created / used workspace (statistics in bb_get_info)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
@@ -172,6 +177,13 @@ Workspace* get_ws(bb_handle* h, cudaStream_t s) {
     cudaGetLastError();
     w->host_flag = nullptr;
   }
+  if (cudaMalloc(reinterpret_cast<void**>(&w->ctl), 256) != cudaSuccess || cudaMemset(w->ctl, 0, 256) != cudaSuccess) {
+    cudaGetLastError();
+    if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
+    delete w;
+    return nullptr;
+  }
+  h->last_ws = w;
   h->ws[s] = w;
   return w;
 }
@@ -324,12 +336,12 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     BB_CUDA(h, cudaMemsetAsync(static_cast<__nv_bfloat16*>(w->q_bf16.p) + static_cast<size_t>(B) * KP, 0,
                                sizeof(__nv_bfloat16) * static_cast<size_t>(plan.b_pad - B) * KP, stream));
   }
-  BB_CUDA(h, cudaMemsetAsync(h->err_dev, 0, sizeof(int32_t), stream));
+  BB_CUDA(h, cudaMemsetAsync(w->err_flag(), 0, sizeof(int32_t), stream));
   BB_CUDA(h, launch_prep_queries(static_cast<const float*>(d_emb), static_cast<const int32_t*>(d_item),
                                  static_cast<const float*>(d_cf), static_cast<const float*>(d_wc),
                                  static_cast<const float*>(d_wf), q->w_content_all, q->w_cf_all, B, D, F, KP,
                                  h->cfg.metric, h->cat_f32, h->cat_bf16, h->cfg.id_offset, h->cfg.n_items,
-                                 static_cast<float*>(w->q_f32.p), w->q_bf16.p, h->err_dev, stream));
+                                 static_cast<float*>(w->q_f32.p), w->q_bf16.p, w->err_flag(), stream));
   h->launches++;
 
   // ---- candidate state
@@ -357,8 +369,9 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.n_sub = tc ? kTcSubStreams : 1;
   P.tile_items = plan.tile_items;
   P.dump = dump;
-  P.stat_candidates = h->stat_dev;
-  P.err_flag = h->err_dev;
+  P.stat_candidates = w->stats();
+  P.err_flag = w->err_flag();
+  h->last_ws = w;
   {
     const char* dbg = getenv("BB_DEBUG_FLAGS");
     P.debug_flags = dbg != nullptr ? atoi(dbg) : 0;
@@ -375,8 +388,8 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
     P.thr_g = static_cast<uint32_t*>(w->thr_g.p);
     BB_CUDA(h, launch_fill_u32(P.thr_g, kOrdNegInf, plan.b_pad, stream));
-    P.wave_counter = reinterpret_cast<uint32_t*>(h->stat_dev + 7);
-    BB_CUDA(h, cudaMemsetAsync(h->stat_dev, 0, 8 * sizeof(unsigned long long), stream));
+    P.wave_counter = w->wave_counter();
+    BB_CUDA(h, cudaMemsetAsync(w->ctl, 0, 128, stream));
     h->launches++;
   }
 
@@ -439,11 +452,11 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
 int check_device_flag(bb_handle* h, Workspace* w, cudaStream_t stream) {
   int32_t flag = 0;
   if (w->host_flag != nullptr) {
-    BB_CUDA(h, cudaMemcpyAsync(w->host_flag, h->err_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    BB_CUDA(h, cudaMemcpyAsync(w->host_flag, w->err_flag(), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     BB_CUDA(h, cudaStreamSynchronize(stream));
     flag = *w->host_flag;
   } else {
-    BB_CUDA(h, cudaMemcpyAsync(&flag, h->err_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    BB_CUDA(h, cudaMemcpyAsync(&flag, w->err_flag(), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     BB_CUDA(h, cudaStreamSynchronize(stream));
   }
   if (flag == 1) return fail(h, BB_ERR_INVALID, "q_item / id outside this shard's id range");
@@ -515,11 +528,6 @@ int bb_create(bb_handle** out, const bb_config* cfg) {
     e = cudaMalloc(reinterpret_cast<void**>(&h->meta), rows * sizeof(int2));
     if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "metadata alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
   }
-  e = cudaMalloc(reinterpret_cast<void**>(&h->stat_dev), 64);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->err_dev), 64);
-  if (e == cudaSuccess) e = cudaMemset(h->stat_dev, 0, 64);
-  if (e == cudaSuccess) e = cudaMemset(h->err_dev, 0, 64);
-  if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "flag alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
   *out = h;
   return BB_OK;
 }
@@ -534,6 +542,7 @@ void bb_destroy(bb_handle* h) {
                       &w->stage, &w->dump, &w->shared_valid})
       b->release();
     if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
+    if (w->ctl != nullptr) cudaFree(w->ctl);
     delete w;
   }
   if (h->cat_f32) cudaFree(h->cat_f32);
@@ -545,8 +554,6 @@ void bb_destroy(bb_handle* h) {
   if (h->allow && h->allow_owned) cudaFree(h->allow);
   for (auto* v : {&h->prof_pending, &h->prof_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-  if (h->stat_dev) cudaFree(h->stat_dev);
-  if (h->err_dev) cudaFree(h->err_dev);
   cudaGetLastError();
   delete h;
 }
@@ -563,7 +570,7 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->launches = h->launches.load();
   info->last_units = h->last_units.load();
   unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  BB_CUDA(h, cudaMemcpy(c, h->stat_dev, sizeof(c), cudaMemcpyDeviceToHost));
+  if (h->last_ws != nullptr) BB_CUDA(h, cudaMemcpy(c, h->last_ws->stats(), sizeof(c), cudaMemcpyDeviceToHost));
   info->last_candidates = static_cast<int64_t>(c[0]);
   info->last_appends = static_cast<int64_t>(c[1]);
   info->last_slow_chunks = static_cast<int64_t>(c[2]);
@@ -619,6 +626,7 @@ int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float
   if (h->cfg.cf_dim > 0 && item_factors == nullptr) return fail(h, BB_ERR_INVALID, "item_factors is NULL but cf_dim=%d", h->cfg.cf_dim);
   const int D = h->cfg.dim, F = h->cfg.cf_dim, KP = h->k_pad;
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const int64_t chunk = 1 << 18;   // staging granularity for host inputs
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
@@ -665,6 +673,7 @@ int bb_fetch_embeddings(bb_handle* h, int32_t n, const int32_t* ids, float* out,
   if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
   if (n <= 0 || ids == nullptr || out == nullptr) return fail(h, BB_ERR_INVALID, "bad arguments");
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   Stager st{h, &w->stage, 0, stream, 0};
   st.account(ids, sizeof(int32_t) * n);
@@ -677,9 +686,9 @@ int bb_fetch_embeddings(bb_handle* h, int32_t n, const int32_t* ids, float* out,
     BB_CUDA(h, w->misc.ensure(sizeof(float) * static_cast<size_t>(n) * h->cfg.dim));
     d_out = static_cast<float*>(w->misc.p);
   }
-  BB_CUDA(h, cudaMemsetAsync(h->err_dev, 0, sizeof(int32_t), stream));
+  BB_CUDA(h, cudaMemsetAsync(w->err_flag(), 0, sizeof(int32_t), stream));
   BB_CUDA(h, launch_gather_rows(h->cat_f32, h->cat_bf16, h->k_pad, h->cfg.dim, h->cfg.id_offset, h->cfg.n_items,
-                                static_cast<const int32_t*>(d_ids), n, d_out, h->err_dev, stream));
+                                static_cast<const int32_t*>(d_ids), n, d_out, w->err_flag(), stream));
   h->launches++;
   if (!out_dev) {
     BB_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(float) * static_cast<size_t>(n) * h->cfg.dim, cudaMemcpyDeviceToHost, stream));
@@ -759,6 +768,7 @@ int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_score
   if (q->precision < BB_PREC_FP32 || q->precision > BB_PREC_BF16_RESCORE) return fail(h, BB_ERR_INVALID, "unknown precision");
 
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
   // k' kept per candidate buffer: a multiple of 32; the re-scored path over-fetches.
@@ -803,6 +813,7 @@ int bb_debug_scores(bb_handle* h, const bb_query_batch* q, float* out_scores, vo
   if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
   if (q->n_queries <= 0) return fail(h, BB_ERR_INVALID, "n_queries must be > 0");
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const size_t bytes = sizeof(float) * static_cast<size_t>(q->n_queries) * h->cfg.n_items;
   const bool dev = is_device_ptr(out_scores);
@@ -828,6 +839,7 @@ int bb_apply_constraints(bb_handle* h, const bb_constraint* constraints, int32_t
   if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
   if (n <= 0 || constraints == nullptr || out_bitmaps == nullptr) return fail(h, BB_ERR_INVALID, "bad arguments");
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const int64_t words = (h->cfg.n_items + 31) / 32;
   Stager st{h, &w->stage, 0, stream, 0};
@@ -875,6 +887,7 @@ int bb_hybrid_combine(bb_handle* h, int32_t n_rows, int32_t len_c, const int32_t
   if ((len_c > 0 && (c_ids == nullptr || c_scores == nullptr)) || (len_f > 0 && (f_ids == nullptr || f_scores == nullptr)))
     return fail(h, BB_ERR_INVALID, "NULL list");
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   Stager st{h, &w->stage, 0, stream, 0};
   const size_t nc = static_cast<size_t>(n_rows) * len_c, nf = static_cast<size_t>(n_rows) * len_f;
@@ -910,6 +923,7 @@ int bb_merge_topk(bb_handle* h, int32_t n_queries, int32_t n_lists, int32_t len,
   if (n_queries <= 0 || n_lists <= 0 || len <= 0 || k <= 0 || k > kMaxSel) return fail(h, BB_ERR_INVALID, "merge_topk: bad shape");
   if (scores == nullptr || ids == nullptr || out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const size_t n_in = static_cast<size_t>(n_lists) * n_queries * len;
   Stager st{h, &w->stage, 0, stream, 0};
@@ -941,6 +955,7 @@ int bb_item_item_topk(bb_handle* h, int64_t n_users, int32_t n_items, const int6
   if (indptr == nullptr || indices == nullptr || values == nullptr || out_scores == nullptr || out_ids == nullptr)
     return fail(h, BB_ERR_INVALID, "NULL argument");
   Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   int64_t nnz = 0;
   if (is_device_ptr(indptr)) BB_CUDA(h, cudaMemcpy(&nnz, indptr + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost));

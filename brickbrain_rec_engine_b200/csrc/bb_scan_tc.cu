@@ -41,12 +41,16 @@ constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata
 constexpr int kThemeBytes = 32 * 128 * 4;         // per-row allowed-theme bitmaps, word-major [32 words][128 rows]
 constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
 
-template <int CG> struct Cfg {
+// kRowCons: the batch carries per-row constraint descriptors that are prefiltered in the epilogue (needs the
+// per-row allowed-theme bitmaps in shared memory); otherwise that space is a sixth TMA stage.
+template <int CG, bool kRowCons> struct Cfg {
   static constexpr int kBRows = kTcTile / CG;            // catalog rows this CTA loads per stage
   static constexpr int kBStageBytes = kBRows * 128;
-  static constexpr int kStages = (CG == 2) ? 5 : 2;
+  static constexpr int kStages = (CG == 2) ? (kRowCons ? 5 : 6) : (kRowCons ? 2 : 3);
+  static constexpr int kThemeSmem = kRowCons ? kThemeBytes : 0;
   static constexpr int kSmemBytes =
-      kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kColMetaBytes + kThemeBytes + 512 + 1024;
+      kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kColMetaBytes + kThemeSmem + 512 + 1024;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -214,11 +218,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int CG>
+template <int CG, bool kRowCons>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                const ScanParams P, const int n_groups) {
-  using C = Cfg<CG>;
+  using C = Cfg<CG, kRowCons>;
   extern __shared__ unsigned char smem_raw[];
   // 1024 B alignment (128B swizzle atoms) by pointer arithmetic on the __shared__ array, so that the compiler keeps
   // the shared address space (integer round-trips degrade every later access to generic LD/ST)
@@ -227,7 +231,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   unsigned char* smem_b = smem + kTcMaxKBlocks * kAkbBytes;
   uint4* smem_colmeta = reinterpret_cast<uint4*>(smem_b + C::kStages * C::kBStageBytes);
   uint32_t* smem_theme = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(smem_colmeta) + kColMetaBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem_theme) + kThemeBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem_theme) + C::kThemeSmem);
   uint64_t* bar_full = bars;                      // [kStages]  TMA -> MMA     (leader's are used)
   uint64_t* bar_empty = bars + C::kStages;        // [kStages]  MMA -> TMA     (per CTA)
   uint64_t* bar_a_full = bars + 2 * C::kStages;   //            TMA -> MMA     (leader)
@@ -374,7 +378,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t* theme_row = smem_theme + row_in_cta;  // this row's allowed-theme words at [w * 128]
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t acc_empty_leader_base = (CG == 2) ? mapa_u32(smem_u32(bar_acc_empty), 0) : smem_u32(bar_acc_empty);
-    const bool use_cons = P.cons != nullptr && P.class_valid == nullptr;   // per-row prefilter (no class bitmaps)
+    const bool use_cons = kRowCons && P.cons != nullptr && P.class_valid == nullptr;   // per-row prefilter (no class bitmaps)
     unsigned stat_appends = 0, stat_slow = 0, stat_compact = 0;   // per-thread / per-warp counters (debug statistics)
     for (int u = group; u < n_units; u += n_groups) {
       const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
@@ -592,27 +596,26 @@ cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* 
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kThreads);
   cfg.stream = stream;
-  cudaError_t e;
-  if (cta_group == 2) {
-    e = cudaFuncSetAttribute(scan_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<2>::kSmemBytes);
+  const bool row_cons = P.cons != nullptr && P.class_valid == nullptr;
+  auto launch = [&](auto kernel, int smem, int cg) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    cfg.gridDim = dim3(n_groups * 2);
-    cfg.dynamicSmemBytes = Cfg<2>::kSmemBytes;
+    cfg.gridDim = dim3(n_groups * cg);
+    cfg.dynamicSmemBytes = smem;
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = cg;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, scan_tc_kernel<2>, *tq, *te, P, n_groups);
+    return cudaLaunchKernelEx(&cfg, kernel, *tq, *te, P, n_groups);
+  };
+  if (cta_group == 2) {
+    return row_cons ? launch(scan_tc_kernel<2, true>, Cfg<2, true>::kSmemBytes, 2)
+                    : launch(scan_tc_kernel<2, false>, Cfg<2, false>::kSmemBytes, 2);
   }
-  e = cudaFuncSetAttribute(scan_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::kSmemBytes);
-  if (e != cudaSuccess) return e;
-  cfg.gridDim = dim3(n_groups);
-  cfg.dynamicSmemBytes = Cfg<1>::kSmemBytes;
-  cfg.attrs = nullptr;
-  cfg.numAttrs = 0;
-  return cudaLaunchKernelEx(&cfg, scan_tc_kernel<1>, *tq, *te, P, n_groups);
+  return row_cons ? launch(scan_tc_kernel<1, true>, Cfg<1, true>::kSmemBytes, 1)
+                  : launch(scan_tc_kernel<1, false>, Cfg<1, false>::kSmemBytes, 1);
 }
 
 }  // namespace bb
