@@ -158,24 +158,59 @@ struct WarpMerger {
   uint64_t* stage;
   int n_new;
   int lane;
+  uint64_t floor_key;      // k'-th best so far: offers at or below it are dropped before they reach the stage
   __device__ void init(uint64_t* s, int l) {
-    stage = s; n_new = 0; lane = l;
+    stage = s; n_new = 0; lane = l; floor_key = 0ull;
     for (int i = lane; i < kCap; i += 32) stage[i] = 0ull;
     __syncwarp();
   }
+  // stage[0..127] is sorted (or empty) and stage[128..] holds <= 128 new keys: sort only the new keys and merge
+  // (one compare against the reversed tail + one bitonic merge phase), as in the scan's compaction.
   __device__ void flush() {
-    uint64_t v[kEpl];
+    constexpr int PE = kEpl / 2;
+    uint64_t p[PE], t[PE];
 #pragma unroll
-    for (int i = 0; i < kEpl; ++i) v[i] = stage[(i << 5) | lane];
+    for (int i = 0; i < PE; ++i) {
+      p[i] = stage[(i << 5) | lane];
+      t[i] = stage[kCap / 2 + ((i << 5) | lane)];
+    }
     __syncwarp();
-    warp_sort_desc<kEpl>(v, lane);
+    warp_sort_desc<PE>(t, lane);
 #pragma unroll
-    for (int i = 0; i < kEpl; ++i) stage[(i << 5) | lane] = (i < kEpl / 2) ? v[i] : 0ull;
+    for (int i = 0; i < PE; ++i) {
+      const uint64_t r = __shfl_sync(kFull, t[PE - 1 - i], 31 - lane);
+      p[i] = p[i] > r ? p[i] : r;
+    }
+    warp_bitonic_merge_desc<PE>(p, lane);
+#pragma unroll
+    for (int i = 0; i < PE; ++i) {
+      stage[(i << 5) | lane] = p[i];
+      stage[kCap / 2 + ((i << 5) | lane)] = 0ull;
+    }
+    floor_key = __shfl_sync(kFull, p[PE - 1], 31);
     n_new = 0;
+    __syncwarp();
+  }
+  // top-128 of this merger's sorted prefix and another sorted 128-key list (pairwise tree merge)
+  __device__ void absorb_sorted(const uint64_t* other) {
+    constexpr int PE = kEpl / 2;
+    uint64_t p[PE];
+#pragma unroll
+    for (int i = 0; i < PE; ++i) {
+      const int e = (i << 5) | lane;
+      const uint64_t r = other[kCap / 2 - 1 - e];
+      const uint64_t a = stage[e];
+      p[i] = a > r ? a : r;
+    }
+    __syncwarp();
+    warp_bitonic_merge_desc<PE>(p, lane);
+#pragma unroll
+    for (int i = 0; i < PE; ++i) stage[(i << 5) | lane] = p[i];
     __syncwarp();
   }
   // every lane offers one key (0 = nothing)
   __device__ void offer(uint64_t key) {
+    if (key <= floor_key) key = 0ull;
     const unsigned m = __ballot_sync(kFull, key != 0ull);
     if (m == 0) return;
     if (key != 0ull) stage[kCap / 2 + n_new + __popc(m & ((1u << lane) - 1u))] = key;
@@ -223,18 +258,19 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     mg.flush();
   }
   __syncthreads();
+  // pairwise tree merge of the four sorted partial tops: (0,1) and (2,3) in parallel, then (0,2)
+  if (warp == 0 || warp == 2) {
+    WarpMerger m2;
+    m2.stage = stage_all[warp];
+    m2.lane = lane;
+    m2.absorb_sorted(stage_all[warp + 1]);
+  }
+  __syncthreads();
   if (warp == 0) {
-    uint64_t mine[kEpl / 2];
-#pragma unroll
-    for (int x = 0; x < kEpl / 2; ++x) mine[x] = stage[(x << 5) | lane];
-    __syncwarp();
-    WarpMerger fin;
-    fin.init(stage, lane);
-#pragma unroll
-    for (int x = 0; x < kEpl / 2; ++x) fin.offer(mine[x]);
-    for (int w = 1; w < 4; ++w)
-      for (int x = 0; x < kCap / 2; x += 32) fin.offer(stage_all[w][x + lane]);
-    fin.flush();
+    WarpMerger m2;
+    m2.stage = stage_all[0];
+    m2.lane = lane;
+    m2.absorb_sorted(stage_all[2]);
   }
   __syncthreads();
 
