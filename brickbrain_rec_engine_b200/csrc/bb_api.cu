@@ -209,7 +209,7 @@ int make_tmap(bb_handle* h, CUtensorMap* out, const void* base, uint64_t rows, i
 }
 
 struct Plan {
-  int n_qblocks, n_tiles, n_splits, n_groups, b_pad, tile_items;
+  int n_qblocks, n_tiles, n_splits, n_groups, b_pad, tile_items, pilot_tiles, n_units;
 };
 
 Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
@@ -252,6 +252,11 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
   p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
+  // pilot: one short unit per query block over the first tiles, before anything else (tcgen05 scan, catalogs
+  // that are long compared with it)
+  p.pilot_tiles = (tc && p.n_tiles >= 640 && getenv("BB_NO_PILOT") == nullptr) ? 32 : 0;
+  const long long pilot_slots = p.pilot_tiles > 0 ? (static_cast<long long>(p.n_qblocks) + p.n_groups - 1) / p.n_groups * p.n_groups : 0;
+  p.n_units = static_cast<int>(pilot_slots + units);
   return p;
 }
 
@@ -367,6 +372,9 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.n_splits = plan.n_splits;
   P.n_tiles = plan.n_tiles;
   P.n_sub = tc ? kTcSubStreams : 1;
+  P.pilot_tiles = dump == nullptr ? plan.pilot_tiles : 0;
+  P.n_slot_splits = plan.n_splits + (P.pilot_tiles > 0 ? 1 : 0);
+  P.n_units = P.pilot_tiles > 0 ? plan.n_units : plan.n_qblocks * plan.n_splits;
   P.tile_items = plan.tile_items;
   P.dump = dump;
   P.stat_candidates = w->stats();
@@ -377,7 +385,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     P.debug_flags = dbg != nullptr ? atoi(dbg) : 0;
   }
   if (dump == nullptr) {
-    const size_t slots = static_cast<size_t>(plan.n_splits) * P.n_sub * plan.b_pad;
+    const size_t slots = static_cast<size_t>(P.n_slot_splits) * P.n_sub * plan.b_pad;
     BB_CUDA(h, w->cand.ensure(slots * kCap * sizeof(uint64_t)));
     BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
     BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
@@ -445,7 +453,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     h->prof_pending.push_back(ev);
   }
   h->launches++;
-  h->last_units = static_cast<long long>(plan.n_qblocks) * plan.n_splits;
+  h->last_units = P.n_units;
   return BB_OK;
 }
 

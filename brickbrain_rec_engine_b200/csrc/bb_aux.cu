@@ -240,7 +240,7 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     WarpMerger mg;
     mg.init(stage_all[warp], lane);
     const uint32_t thr = __ldcg(P.thr_g + q);
-    const int n_slots = P.n_splits * P.n_sub;
+    const int n_slots = P.n_slot_splits * P.n_sub;
     for (int s0 = warp * 32; s0 < n_slots; s0 += 128) {
       const int my_s = s0 + lane;
       const int my_cnt = my_s < n_slots ? __ldcg(P.cand_cnt + static_cast<int64_t>(my_s) * P.b_pad + q) : 0;

@@ -140,9 +140,12 @@ struct ScanParams {
   uint32_t* thr_g;        // per-row shared running threshold (ordered bits), raised by every stream of the row
   // schedule
   int32_t n_qblocks;      // query blocks
-  int32_t n_splits;       // catalog splits (units = n_qblocks * n_splits)
+  int32_t n_splits;       // catalog splits of the tiles after the pilot (regular units = n_qblocks * n_splits)
   int32_t n_tiles;        // catalog tiles of tile_items rows
   int32_t tile_items;
+  int32_t pilot_tiles;    // leading tiles scanned by ONE unit per query block before everything else (0 = none)
+  int32_t n_slot_splits;  // n_splits (+1 when there is a pilot): candidate-buffer rows per (sub, query)
+  int32_t n_units;        // unit indices to walk (pilot wave incl. idle slots + regular units)
   // debug
   float* dump;            // dense [b x n_items] score dump (bb_debug_scores) or nullptr
   unsigned long long* stat_candidates;
@@ -152,8 +155,37 @@ struct ScanParams {
 };
 
 __device__ __forceinline__ void split_tile_range(const ScanParams& P, int split, int& t0, int& t1) {
-  t0 = static_cast<int>((static_cast<int64_t>(P.n_tiles) * split) / P.n_splits);
-  t1 = static_cast<int>((static_cast<int64_t>(P.n_tiles) * (split + 1)) / P.n_splits);
+  const int64_t n = P.n_tiles - P.pilot_tiles;
+  t0 = P.pilot_tiles + static_cast<int>((n * split) / P.n_splits);
+  t1 = P.pilot_tiles + static_cast<int>((n * (split + 1)) / P.n_splits);
+}
+
+// Work unit u -> (query block, candidate-slot row, tile range).  With a pilot, the first wave holds one short unit
+// per query block over the leading tiles (all other CTA groups idle for those few microseconds): every stream of
+// the following waves then starts from a threshold instead of cold.
+struct UnitInfo {
+  int qb, split_slot, t0, t1;
+  bool valid;
+};
+__device__ __forceinline__ UnitInfo decode_unit(const ScanParams& P, int u, int n_groups) {
+  UnitInfo r;
+  if (P.pilot_tiles > 0) {
+    const int n_pilot_slots = ((P.n_qblocks + n_groups - 1) / n_groups) * n_groups;
+    if (u < n_pilot_slots) {
+      r.valid = u < P.n_qblocks;
+      r.qb = u;
+      r.split_slot = P.n_splits;
+      r.t0 = 0;
+      r.t1 = P.pilot_tiles;
+      return r;
+    }
+    u -= n_pilot_slots;
+  }
+  r.valid = true;
+  r.qb = u % P.n_qblocks;
+  r.split_slot = u / P.n_qblocks;
+  split_tile_range(P, r.split_slot, r.t0, r.t1);
+  return r;
 }
 
 // ---------------------------------------------------------------- hard-constraint predicate
@@ -307,7 +339,7 @@ __device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, i
 // the max of their local ones.
 constexpr int kRefineSlots = 128;
 __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, int row, int lane) {
-  const int n_slots = P.n_splits * P.n_sub;
+  const int n_slots = P.n_slot_splits * P.n_sub;
   if (n_slots <= 1) return 0u;
   const int stride = (n_slots + kRefineSlots - 1) / kRefineSlots;
   const int n_use = (n_slots + stride - 1) / stride;

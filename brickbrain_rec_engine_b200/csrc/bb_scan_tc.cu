@@ -245,7 +245,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   const bool leader = cta_rank == 0;
   const int group = blockIdx.x / CG;
   const int n_kb = P.k_pad / kBlockK;
-  const int n_units = P.n_qblocks * P.n_splits;
+  const int n_units = P.n_units;
   int32_t* err = P.err_flag;
 
   if (tid == 0) {
@@ -278,15 +278,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint32_t a_full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_a_full), 0) : smem_u32(bar_a_full);
       int wave = 0;
       for (int u = group; u < n_units; u += n_groups, ++wave) {
-        const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
-        int t0, t1;
-        split_tile_range(P, split, t0, t1);
+        const UnitInfo ui = decode_unit(P, u, n_groups);
+        const int qb = ui.qb, t0 = ui.t0, t1 = ui.t1;
         const int row0 = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta;
         // wave barrier: the query blocks that stream the same catalog split share it through L2 only while they
         // stay in step; do not start wave w before every CTA issued all loads of wave w-1 (all CTAs are
         // co-resident: the grid never exceeds one CTA per SM)
         if (wave > 0 && P.wave_counter != nullptr && !(P.debug_flags & 4)) {
-          const uint32_t target = static_cast<uint32_t>(min(wave * n_groups, n_units)) * CG;
+          const uint32_t target = static_cast<uint32_t>(min(wave * n_groups, n_units)) * CG;   // idle pilot slots count too
           const long long t0w = clock64();
           while (*reinterpret_cast<volatile uint32_t*>(P.wave_counter) < target) {
             __nanosleep(200);
@@ -296,6 +295,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
               __trap();
             }
           }
+        }
+        if (!ui.valid) {                               // idle slot of the pilot wave: only take part in the barrier
+          if (P.wave_counter != nullptr) atomicAdd(P.wave_counter, 1u);
+          continue;
         }
         // resident query operand: wait until the previous unit's MMAs stopped reading it
         mbar_wait(smem_u32(bar_a_empty), a_phase ^ 1, err, 101);
@@ -325,9 +328,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       long long t_acc_wait = 0, t_full_wait = 0;     // pipeline triage: who makes the MMA issuer wait
       const long long t_begin = clock64();
       for (int u = group; u < n_units; u += n_groups) {
-        const int split = u / P.n_qblocks;
-        int t0, t1;
-        split_tile_range(P, split, t0, t1);
+        const UnitInfo ui = decode_unit(P, u, n_groups);
+        if (!ui.valid) continue;
+        const int t0 = ui.t0, t1 = ui.t1;
         mbar_wait(smem_u32(bar_a_full), a_phase, err, 103);
         a_phase ^= 1;
         for (int t = t0; t < t1; ++t) {
@@ -381,9 +384,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const bool use_cons = kRowCons && P.cons != nullptr && P.class_valid == nullptr;   // per-row prefilter (no class bitmaps)
     unsigned stat_appends = 0, stat_slow = 0, stat_compact = 0;   // per-thread / per-warp counters (debug statistics)
     for (int u = group; u < n_units; u += n_groups) {
-      const int qb = u % P.n_qblocks, split = u / P.n_qblocks;
-      int t0, t1;
-      split_tile_range(P, split, t0, t1);
+      const UnitInfo ui = decode_unit(P, u, n_groups);
+      if (!ui.valid) continue;
+      const int qb = ui.qb, split = ui.split_slot, t0 = ui.t0, t1 = ui.t1;
       const int q = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta + row_in_cta;
       const bool q_valid = q < P.n_queries;
       // the row's cheap predicates (integer ranges + allowed-theme bitmap) live in registers / smem so that a
@@ -564,7 +567,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
         const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt >= 8);
         // (one of the row's column-slice streams refines; the others only sort + publish)
-        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, half == 0);
+        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, half == 0 && !(P.debug_flags & 8));
         P.cand_cnt[slot] = st.cnt;
         if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
       }
