@@ -224,13 +224,13 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   if (p.n_tiles < 1) p.n_tiles = 1;
   const int hw_groups = tc ? h->sm_count / h->cta_group : h->sm_count * 2;
   // Catalog splits.  Every unit pays a fixed price (cold candidate streams, a sorted + published prefix at its end),
-  // so units should be long (>= ~512 tiles) but there must be enough of them to fill the machine evenly: pick the
+  // so units should be long (>= ~131k catalog rows) but there must be enough of them to fill the machine evenly: pick the
   // smallest split count within reach whose static round-robin schedule keeps >= 97% of the CTA groups busy.
   const long long mem_cap = (5ll << 29) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? kTcSubStreams : 1));   // 2.5 GiB
   long long s_cap = p.n_tiles;
   if (s_cap > 64) s_cap = 64;
   if (s_cap > mem_cap) s_cap = mem_cap > 0 ? mem_cap : 1;
-  long long s_lo = p.n_tiles / 512;
+  long long s_lo = p.n_tiles / (131072 / p.tile_items);     // ~131k catalog rows per unit
   const long long s_fill = (hw_groups + p.n_qblocks - 1) / p.n_qblocks;    // enough units to occupy every group once
   if (s_lo < s_fill) s_lo = s_fill;
   if (s_lo < 1) s_lo = 1;
@@ -252,9 +252,9 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
   p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
-  // pilot: one short unit per query block over the first tiles, before anything else (tcgen05 scan, catalogs
-  // that are long compared with it)
-  p.pilot_tiles = (tc && p.n_tiles >= 640 && getenv("BB_NO_PILOT") == nullptr) ? 32 : 0;
+  // pilot: one short unit per query block over the first tiles, before anything else.  Measured neutral on B200
+  // (cold streams already share thresholds through the early publishes), so it is opt-in: BB_PILOT=1.
+  p.pilot_tiles = (tc && h->cfg.n_items >= 163840 && getenv("BB_PILOT") != nullptr) ? 8192 / p.tile_items : 0;
   const long long pilot_slots = p.pilot_tiles > 0 ? (static_cast<long long>(p.n_qblocks) + p.n_groups - 1) / p.n_groups * p.n_groups : 0;
   p.n_units = static_cast<int>(pilot_slots + units);
   return p;

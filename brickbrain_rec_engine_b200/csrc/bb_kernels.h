@@ -15,7 +15,7 @@ constexpr int kFp32Tile = 128;    // catalog rows per tile
 cudaError_t launch_scan_fp32(const ScanParams& P, const float* Q, const float* E, cudaStream_t stream);
 
 // ---- K1 tcgen05 bf16 scan (bb_scan_tc.cu)
-constexpr int kTcTile = 256;      // catalog rows per MMA tile (UMMA N)
+constexpr int kTcTile = 256;      // catalog rows per MMA tile (UMMA N); 512 / kTcTile TMEM accumulator stages (N=128 is smem-bandwidth bound: measured 995 vs 1524 TFLOP/s MMA-only)
 constexpr int kTcRowsPerCta = 128;
 constexpr int kTcMaxKBlocks = 7;  // resident query operand: 7 x 64 bf16 columns
 constexpr int kTcSubStreams = 4;  // epilogue warps per TMEM lane quarter = candidate streams per (split, row)

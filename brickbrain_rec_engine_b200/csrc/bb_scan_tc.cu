@@ -31,7 +31,8 @@ namespace {
 constexpr int kBlockK = 64;                 // bf16 columns per k-block (= one 128 B swizzle row)
 constexpr int kAkbBytes = 128 * 128;        // resident query k-block: 128 rows x 128 B
 constexpr int kUmmaK = 16;
-constexpr int kAccCols = 256;               // fp32 accumulator columns per tile
+constexpr int kAccCols = kTcTile;           // fp32 accumulator columns per tile
+constexpr int kAccStages = 512 / kAccCols;  // TMEM accumulator ring: how far the MMA issuer may run ahead of the epilogue
 constexpr int kTmemCols = 512;              // two accumulators
 constexpr int kEpiWarps = 4 * kTcSubStreams; // kTcSubStreams warps per TMEM lane quarter, each scans a column slice of every tile
 constexpr int kThreads = (4 + kEpiWarps) * 32;
@@ -46,7 +47,8 @@ constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GP
 template <int CG, bool kRowCons> struct Cfg {
   static constexpr int kBRows = kTcTile / CG;            // catalog rows this CTA loads per stage
   static constexpr int kBStageBytes = kBRows * 128;
-  static constexpr int kStages = (CG == 2) ? (kRowCons ? 5 : 6) : (kRowCons ? 2 : 3);
+  static constexpr int kStages = (CG == 2) ? (kRowCons ? 80 : 96) * 1024 / kBStageBytes
+                                           : (kRowCons ? 64 : 96) * 1024 / kBStageBytes;
   static constexpr int kThemeSmem = kRowCons ? kThemeBytes : 0;
   static constexpr int kSmemBytes =
       kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kColMetaBytes + kThemeSmem + 512 + 1024;
@@ -236,9 +238,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* bar_empty = bars + C::kStages;        // [kStages]  MMA -> TMA     (per CTA)
   uint64_t* bar_a_full = bars + 2 * C::kStages;   //            TMA -> MMA     (leader)
   uint64_t* bar_a_empty = bar_a_full + 1;         //            MMA -> TMA     (per CTA)
-  uint64_t* bar_acc_full = bar_a_full + 2;        // [2]        MMA -> epilogue (per CTA)
-  uint64_t* bar_acc_empty = bar_a_full + 4;       // [2]        epilogue -> MMA (leader)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a_full + 6);
+  uint64_t* bar_acc_full = bar_a_full + 2;                     // [kAccStages]  MMA -> epilogue (per CTA)
+  uint64_t* bar_acc_empty = bar_acc_full + kAccStages;         // [kAccStages]  epilogue -> MMA (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + kAccStages);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -255,7 +257,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
     mbar_init(smem_u32(bar_a_full), 1);
     mbar_init(smem_u32(bar_a_empty), 1);
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kAccStages; ++a) {
       mbar_init(smem_u32(bar_acc_full + a), 1);
       mbar_init(smem_u32(bar_acc_empty + a), CG * kEpiWarps);
     }
@@ -360,8 +362,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           if (lane == 0) umma_commit<CG>(smem_u32(bar_acc_full + acc));   // accumulator ready
           __syncwarp();
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
         if (lane == 0) umma_commit<CG>(smem_u32(bar_a_empty));            // query operand no longer read
         __syncwarp();
@@ -558,8 +559,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           const unsigned early = __ballot_sync(kFull, pub_now);
           stat_compact += warp_compact_if_needed(P, st, q, lane, early, true, 32 * kChunksPerWarp);
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
       if (P.dump == nullptr) {
         // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units

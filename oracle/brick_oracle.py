@@ -447,23 +447,40 @@ def batched_cpu_topk(q_cat: np.ndarray, e_cat: np.ndarray, k: int,
                      valid: Optional[np.ndarray] = None, block: int = 65536) -> Tuple[np.ndarray, np.ndarray]:
     """Best-effort CPU restatement used as ``cpu_baseline`` (kind "port"):
     blocked fp32 sgemm (all BLAS threads) over the concatenated operands
-    [w_c*q_hat | w_f*u] x [e_hat | v], optional [N] validity mask, running
-    top-k by argpartition.  BASELINE.md section 4 item 2."""
+    [w_c*q_hat | w_f*u] x [e_hat | v], optional [N] validity mask, and a running
+    top-k: the first block is partitioned, later blocks only keep scores above each
+    row's current k-th best (vectorized compare + one sort of the survivors), so the
+    selection cost stays well below the sgemm.  BASELINE.md section 4 item 2."""
     b = q_cat.shape[0]
     n = e_cat.shape[0]
     best_s = np.full((b, k), -np.inf, dtype=np.float32)
     best_i = np.full((b, k), -1, dtype=np.int64)
+    penalty = None if valid is None else np.where(valid, np.float32(0), np.float32(-np.inf)).astype(np.float32)
     for lo in range(0, n, block):
         hi = min(n, lo + block)
         s = q_cat @ e_cat[lo:hi].T
-        if valid is not None:
-            s[:, ~valid[lo:hi]] = -np.inf
-        kk = min(k, hi - lo)
-        part = np.argpartition(-s, kk - 1, axis=1)[:, :kk]
-        cand_s = np.concatenate([best_s, np.take_along_axis(s, part, axis=1)], axis=1)
-        cand_i = np.concatenate([best_i, part + lo], axis=1)
-        sel = np.argpartition(-cand_s, k - 1, axis=1)[:, :k]
-        best_s = np.take_along_axis(cand_s, sel, axis=1)
-        best_i = np.take_along_axis(cand_i, sel, axis=1)
+        if penalty is not None:
+            s += penalty[None, lo:hi]
+        if lo == 0:
+            kk = min(k, hi - lo)
+            part = np.argpartition(-s, kk - 1, axis=1)[:, :kk]
+            best_s[:, :kk] = np.take_along_axis(s, part, axis=1)
+            best_i[:, :kk] = part
+            continue
+        thr = best_s.min(axis=1)
+        rows, cols = np.nonzero(s > thr[:, None])
+        if rows.size == 0:
+            continue
+        # merge the survivors with the running lists: one sort by (row, -score), keep the first k per row
+        all_r = np.concatenate([np.repeat(np.arange(b), k), rows])
+        all_s = np.concatenate([best_s.ravel(), s[rows, cols]])
+        all_i = np.concatenate([best_i.ravel(), cols + lo])
+        order = np.lexsort((-all_s, all_r))
+        all_r, all_s, all_i = all_r[order], all_s[order], all_i[order]
+        start = np.searchsorted(all_r, np.arange(b))
+        rank = np.arange(all_r.size) - start[all_r]
+        keep = rank < k
+        best_s = all_s[keep].reshape(b, k)
+        best_i = all_i[keep].reshape(b, k)
     order = np.lexsort((best_i, -best_s), axis=1)
     return np.take_along_axis(best_i, order, axis=1), np.take_along_axis(best_s, order, axis=1)
