@@ -249,6 +249,10 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
       splits = sc;
     }
   }
+  if (const char* ov = getenv("BB_SPLITS")) {      // experimentation override
+    const long long v = atoll(ov);
+    if (v >= 1 && v <= s_cap) splits = v;
+  }
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
   p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
