@@ -493,7 +493,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           float m = __uint_as_float(r[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-          if (__any_sync(kFull, m >= st.thr) && !(P.debug_flags & 1)) {
+          // (class mode: a row whose constraint set admits none of this chunk's 32 items cannot have a candidate,
+          //  whatever its scores -- selective rows then stop dragging their warp into the slow path)
+          if (__any_sync(kFull, m >= st.thr && class_word != 0u) && !(P.debug_flags & 1)) {
             // ---- slow path, entered only when some row of this warp has a score >= its threshold
             ++stat_slow;
             unsigned pm = 0;                                   // per row: columns whose score passes
