@@ -559,7 +559,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           const bool pub_now = !dead && st.thr == -INFINITY && st.cnt >= next_pub;
           if (pub_now) next_pub *= 2;                // 32, 64, 128, then only the regular overflow trigger
           const unsigned early = __ballot_sync(kFull, pub_now);
-          stat_compact += warp_compact_if_needed(P, st, q, lane, early, true, 32 * kChunksPerWarp);
+          // (in-scan compactions only publish; measured: refining here costs more stall than the tighter threshold saves --
+          //  the refinement at unit end is what keeps later units warm)
+          stat_compact += warp_compact_if_needed(P, st, q, lane, early, (P.debug_flags & 16) != 0, 32 * kChunksPerWarp);
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
