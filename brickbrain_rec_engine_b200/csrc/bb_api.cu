@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/brickscore.h"
@@ -58,6 +59,8 @@ struct Workspace {
   const void* tmap_q_ptr = nullptr;
   int tmap_q_rows = 0;
   int32_t* host_flag = nullptr;   // pinned
+  std::vector<bb_constraint> dedup_cons;   // host-side de-duplication of per-query descriptors (class mode)
+  std::vector<int32_t> dedup_idx;
   // per-stream control block on the device (concurrent searches on other streams must not share these):
   // bytes [0,64) statistics, [64,68) wave-barrier counter, [128,132) error / watchdog flag
   unsigned char* ctl = nullptr;
@@ -313,6 +316,33 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     }
   }
 
+  // ---- per-query descriptors in host memory: queries that share a constraint set (popular filters) are folded
+  //      into distinct sets + a per-query index, which selects the class-bitmap path of the scan
+  const bb_constraint* q_cons = q->constraints;
+  const int32_t* q_cidx = q->constraint_index;
+  int n_cons = q->n_constraints;
+  if (tc && dump == nullptr && q_cidx == nullptr && n_cons == B && B > 1 && !is_device_ptr(q_cons)) {
+    std::unordered_map<std::string, int32_t> seen;
+    w->dedup_cons.clear();
+    w->dedup_idx.resize(B);
+    bool few = true;
+    for (int i = 0; i < B && few; ++i) {
+      std::string key(reinterpret_cast<const char*>(q_cons + i), sizeof(bb_constraint));
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        if (w->dedup_cons.size() >= 64) { few = false; break; }
+        it = seen.emplace(std::move(key), static_cast<int32_t>(w->dedup_cons.size())).first;
+        w->dedup_cons.push_back(q_cons[i]);
+      }
+      w->dedup_idx[i] = it->second;
+    }
+    if (few) {
+      q_cons = w->dedup_cons.data();
+      q_cidx = w->dedup_idx.data();
+      n_cons = static_cast<int>(w->dedup_cons.size());
+    }
+  }
+
   // ---- stage host inputs
   Stager st{h, &w->stage, 0, stream, 0};
   st.account(q->q_emb, sizeof(float) * B * D);
@@ -320,9 +350,9 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   st.account(q->q_cf, sizeof(float) * B * F);
   st.account(q->w_content, sizeof(float) * B);
   st.account(q->w_cf, sizeof(float) * B);
-  st.account(q->constraints, sizeof(bb_constraint) * q->n_constraints);
+  st.account(q_cons, sizeof(bb_constraint) * n_cons);
   st.account(q->self_id, sizeof(int32_t) * B);
-  st.account(q->constraint_index, sizeof(int32_t) * B);
+  st.account(q_cidx, sizeof(int32_t) * B);
   BB_CUDA(h, w->stage.ensure(st.need + 256));
   const void *d_emb, *d_item, *d_cf, *d_wc, *d_wf, *d_cons, *d_self, *d_cidx;
   BB_CUDA(h, st.get(q->q_emb, sizeof(float) * B * D, &d_emb));
@@ -330,9 +360,9 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   BB_CUDA(h, st.get(q->q_cf, sizeof(float) * B * F, &d_cf));
   BB_CUDA(h, st.get(q->w_content, sizeof(float) * B, &d_wc));
   BB_CUDA(h, st.get(q->w_cf, sizeof(float) * B, &d_wf));
-  BB_CUDA(h, st.get(q->constraints, sizeof(bb_constraint) * q->n_constraints, &d_cons));
+  BB_CUDA(h, st.get(q_cons, sizeof(bb_constraint) * n_cons, &d_cons));
   BB_CUDA(h, st.get(q->self_id, sizeof(int32_t) * B, &d_self));
-  BB_CUDA(h, st.get(q->constraint_index, sizeof(int32_t) * B, &d_cidx));
+  BB_CUDA(h, st.get(q_cidx, sizeof(int32_t) * B, &d_cidx));
 
   // ---- query operands
   const size_t qf_bytes = sizeof(float) * static_cast<size_t>(plan.b_pad) * KP;
@@ -363,7 +393,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.k_pad = KP;
   P.k_sel = k_sel;
   P.cons = static_cast<const bb_constraint*>(d_cons);
-  P.cons_stride = (q->constraint_index == nullptr && q->n_constraints == B && B > 1) ? 1 : 0;
+  P.cons_stride = (q_cidx == nullptr && n_cons == B && B > 1) ? 1 : 0;
   P.cons_index = static_cast<const int32_t*>(d_cidx);
   P.self_id = static_cast<const int32_t*>(d_self);
   P.theme_sets = h->theme_sets;
@@ -408,7 +438,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
   //      set once per item with the mask kernel (K3); the scan epilogue then masks a 32-item chunk of a row with
   //      one word of its set's bitmap
-  const int n_classes = (q->n_constraints == 1 && B > 1) ? 1 : (q->constraint_index != nullptr ? q->n_constraints : 0);
+  const int n_classes = (n_cons == 1 && B > 1) ? 1 : (q_cidx != nullptr ? n_cons : 0);
   if (tc && dump == nullptr && n_classes >= 1 && n_classes <= 64) {
     const int64_t words = (h->cfg.n_items + 31) / 32;
     const size_t bm_bytes = static_cast<size_t>(n_classes) * words * sizeof(uint32_t);

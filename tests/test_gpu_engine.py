@@ -136,6 +136,12 @@ def test_fused_hybrid_topk_with_constraints(bb, precision):
     s2, i2 = eng.search(k, q_item=q_items, q_cf=u, w_content=0.4, w_cf=0.6, constraints=distinct, constraint_index=index,
                         self_id=q_items, precision=precision)
     assert np.array_equal(i2, ids) and np.array_equal(s2, scores)
+    # device-resident per-query descriptors are not de-duplicated: this exercises the per-row prefilter of the epilogue
+    import torch
+    dev_desc = torch.from_numpy(descs.view(np.uint8).reshape(b, -1).copy()).cuda()
+    s3, i3 = eng.search(k, q_item=torch.from_numpy(q_items).cuda(), q_cf=torch.from_numpy(u).cuda(), w_content=0.4, w_cf=0.6,
+                        constraints=dev_desc, self_id=torch.from_numpy(q_items).cuda(), precision=precision)
+    assert np.array_equal(i3.cpu().numpy(), ids) and np.array_equal(s3.cpu().numpy(), scores)
     eng.close()
 
 
