@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--constraint-form", default="indexed", choices=["indexed", "per-query"],
                    help="indexed: distinct constraint sets + per-query index (class bitmaps); per-query: one descriptor per query")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-share", action="store_true", help="N>1: do not share running thresholds between the shards")
     p.add_argument("--cpu-sample-items", type=int, default=1_000_000)
     p.add_argument("--cpu-sample-queries", type=int, default=1024)
     return p.parse_args()
@@ -189,6 +190,11 @@ def run_ours(args):
     # ---------------- resident catalog shard (synthetic, generated on the device)
     lo, hi = shard_bounds(n, world, rank)
     eng = ScoringEngine(hi - lo, d, f, device=local, id_offset=lo, k_max=128, max_batch=b)
+    # row-sharded catalog: the shards' per-query running thresholds are one logical array over NVLink peer memory
+    share = False
+    if world > 1 and not args.no_share:
+        from brickbrain_rec_engine_b200.sharded import exchange_threshold_handles
+        share = exchange_threshold_handles(eng)
     descs, theme_bitmaps, themes = scenario_descriptors(b)
     eng.set_theme_sets(theme_bitmaps)
     # queries carry (index into) the batch's distinct constraint sets; --distinct-constraints per-query disables it
@@ -233,7 +239,7 @@ def run_ours(args):
         qd = devq[i & 1]
         eng.search(k, q_emb=qd["q"], q_cf=qd["u"], w_content=0.4, w_cf=0.6, constraints=qd["cons"],
                    constraint_index=qd["cidx"] if indexed else None, self_id=qd["self_id"], precision=args.precision,
-                   out=(out_s, out_i))
+                   out=(out_s, out_i), share_thresholds=share)
         if world > 1:
             dist.all_gather_into_tensor(gather_s.view(-1), out_s.view(-1))
             dist.all_gather_into_tensor(gather_i.view(-1), out_i.view(-1))
@@ -251,7 +257,8 @@ def run_ours(args):
                                 precision=args.precision, out=(host_out_s.numpy(), host_out_i.numpy()))
             return s, ids
         eng.search(k, q_emb=qh["q"].numpy(), q_cf=qh["u"].numpy(), w_content=0.4, w_cf=0.6, constraints=cons_np,
-                   constraint_index=cidx_np, self_id=qh["self_id"].numpy(), precision=args.precision, out=(out_s, out_i))
+                   constraint_index=cidx_np, self_id=qh["self_id"].numpy(), precision=args.precision, out=(out_s, out_i),
+                   share_thresholds=share)
         dist.all_gather_into_tensor(gather_s.view(-1), out_s.view(-1))
         dist.all_gather_into_tensor(gather_i.view(-1), out_i.view(-1))
         ms, mi = eng.merge_topk(gather_s, gather_i, k)
@@ -334,7 +341,7 @@ def run_ours(args):
                                f"{distinct.shape[0]} constraint sets" + (" + per-query index" if indexed else "") +
                                f"), self exclusion, top-{k}",
                    "n_items": n, "batch": b, "k": k, "dim": d, "cf_dim": f, "precision": args.precision,
-                   "constraint_form": args.constraint_form, "parallelism": f"row-sharded catalog x{world}" + (" + NCCL all-gather top-k merge" if world > 1 else ""),
+                   "constraint_form": args.constraint_form, "parallelism": f"row-sharded catalog x{world}" + (" + NCCL all-gather top-k merge" if world > 1 else "") + (" + NVLink-shared running thresholds" if share else ""),
                    "l2_policy": f"catalog shard ({(hi - lo) * (d + f) * 2 / 1e9:.2f} GB bf16) is larger than L2 (126 MB); "
                                 "query batches alternate"},
         "clocks": clocks,

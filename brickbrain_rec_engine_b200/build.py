@@ -41,11 +41,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     jobs = []
+    # BB_EPILOGUE_PROFILE=1: compile the scan's epilogue cycle counters in (bb_info.epilogue_cycles); use with --force
+    extra = ["-DBB_EPILOGUE_PROFILE=1"] if os.environ.get("BB_EPILOGUE_PROFILE") == "1" else []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + hdrs):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

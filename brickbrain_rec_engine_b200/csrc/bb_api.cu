@@ -65,8 +65,8 @@ struct Workspace {
   // bytes [0,64) statistics, [64,68) wave-barrier counter, [128,132) error / watchdog flag
   unsigned char* ctl = nullptr;
   unsigned long long* stats() const { return reinterpret_cast<unsigned long long*>(ctl); }
-  uint32_t* wave_counter() const { return reinterpret_cast<uint32_t*>(ctl + 64); }
-  int32_t* err_flag() const { return reinterpret_cast<int32_t*>(ctl + 128); }
+  uint32_t* wave_counter() const { return reinterpret_cast<uint32_t*>(ctl + 128); }
+  int32_t* err_flag() const { return reinterpret_cast<int32_t*>(ctl + 192); }
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -102,6 +102,12 @@ struct bb_handle {
   std::atomic<long long> launches{0};
   std::atomic<long long> last_units{0};
   Workspace* last_ws = nullptr;   // most recently created / used workspace (statistics in bb_get_info)
+  unsigned long long* thr_shared = nullptr;   // per-handle threshold words (exportable to peer ranks), max_batch rows
+  int thr_shared_rows = 0;
+  unsigned long long* peer_thr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int n_peers = 0;
+  std::atomic<uint32_t> epoch{0};          // private searches
+  std::atomic<uint32_t> shared_epoch{0};   // collective searches (BB_Q_SHARE_THRESHOLDS): same sequence on all ranks
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
@@ -425,14 +431,28 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
     BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
     P.pub_cnt = static_cast<int32_t*>(w->pub_cnt.p);
-    BB_CUDA(h, w->thr_g.ensure(static_cast<size_t>(plan.b_pad) * sizeof(uint32_t)));
+    // collective search of a row-sharded catalog: the threshold words live in the exported per-handle array and
+    // carry the collective sequence number; every other search uses the workspace's private array
+    const bool shared = (q->flags & BB_Q_SHARE_THRESHOLDS) != 0 && h->n_peers > 0 && plan.b_pad <= h->thr_shared_rows;
+    if (!shared) {
+      const size_t before = w->thr_g.cap;
+      BB_CUDA(h, w->thr_g.ensure(static_cast<size_t>(plan.b_pad) * sizeof(unsigned long long)));
+      if (w->thr_g.cap != before) BB_CUDA(h, cudaMemsetAsync(w->thr_g.p, 0, w->thr_g.cap, stream));   // epoch 0 = never current
+    }
     P.cand = static_cast<uint64_t*>(w->cand.p);
     P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
-    P.thr_g = static_cast<uint32_t*>(w->thr_g.p);
-    BB_CUDA(h, launch_fill_u32(P.thr_g, kOrdNegInf, plan.b_pad, stream));
+    if (shared) {
+      P.epoch = ++h->shared_epoch;
+      P.thr_g = h->thr_shared;
+      P.n_peers = h->n_peers;
+      for (int i = 0; i < h->n_peers; ++i) P.peer_thr[i] = h->peer_thr[i];
+    } else {
+      P.epoch = ++h->epoch;
+      P.thr_g = static_cast<unsigned long long*>(w->thr_g.p);
+      P.n_peers = 0;
+    }
     P.wave_counter = w->wave_counter();
-    BB_CUDA(h, cudaMemsetAsync(w->ctl, 0, 128, stream));
-    h->launches++;
+    BB_CUDA(h, cudaMemsetAsync(w->ctl, 0, 192, stream));
   }
 
   // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
@@ -570,7 +590,47 @@ int bb_create(bb_handle** out, const bb_config* cfg) {
     e = cudaMalloc(reinterpret_cast<void**>(&h->meta), rows * sizeof(int2));
     if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "metadata alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
   }
+  if (cfg->max_batch > 0) {
+    h->thr_shared_rows = (cfg->max_batch + 255) / 256 * 256;
+    e = cudaMalloc(reinterpret_cast<void**>(&h->thr_shared), static_cast<size_t>(h->thr_shared_rows) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->thr_shared, 0, static_cast<size_t>(h->thr_shared_rows) * sizeof(unsigned long long));
+    if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "threshold array alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+  }
   *out = h;
+  return BB_OK;
+}
+
+int bb_export_threshold_handle(bb_handle* h, void* out_handle) {
+  if (h == nullptr || out_handle == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (h->thr_shared == nullptr) return fail(h, BB_ERR_STATE, "threshold sharing needs bb_config.max_batch > 0");
+  static_assert(sizeof(cudaIpcMemHandle_t) == BB_IPC_HANDLE_BYTES, "ipc handle size");
+  cudaIpcMemHandle_t hd;
+  BB_CUDA(h, cudaIpcGetMemHandle(&hd, h->thr_shared));
+  std::memcpy(out_handle, &hd, sizeof(hd));
+  return BB_OK;
+}
+
+int bb_import_peer_thresholds(bb_handle* h, int32_t n_peers, const void* handles) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && handles == nullptr)) return fail(h, BB_ERR_INVALID, "n_peers must be in [0, 7]");
+  if (h->thr_shared == nullptr) return fail(h, BB_ERR_STATE, "threshold sharing needs bb_config.max_batch > 0");
+  BB_CUDA(h, cudaDeviceSynchronize());
+  for (int i = 0; i < h->n_peers; ++i) cudaIpcCloseMemHandle(h->peer_thr[i]);
+  h->n_peers = 0;
+  for (int i = 0; i < n_peers; ++i) {
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, static_cast<const unsigned char*>(handles) + static_cast<size_t>(i) * sizeof(hd), sizeof(hd));
+    void* p = nullptr;
+    BB_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_thr[h->n_peers++] = static_cast<unsigned long long*>(p);
+  }
+  // a (re-)import restarts the collective sequence on every rank
+  h->shared_epoch = 0;
+  BB_CUDA(h, cudaMemset(h->thr_shared, 0, static_cast<size_t>(h->thr_shared_rows) * sizeof(unsigned long long)));
   return BB_OK;
 }
 
@@ -587,6 +647,8 @@ void bb_destroy(bb_handle* h) {
     if (w->ctl != nullptr) cudaFree(w->ctl);
     delete w;
   }
+  for (int i = 0; i < h->n_peers; ++i) cudaIpcCloseMemHandle(h->peer_thr[i]);
+  if (h->thr_shared) cudaFree(h->thr_shared);
   if (h->cat_f32) cudaFree(h->cat_f32);
   if (h->cat_bf16) cudaFree(h->cat_bf16);
   if (h->meta) cudaFree(h->meta);
@@ -611,7 +673,7 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->cta_group = h->cta_group;
   info->launches = h->launches.load();
   info->last_units = h->last_units.load();
-  unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long c[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (h->last_ws != nullptr) BB_CUDA(h, cudaMemcpy(c, h->last_ws->stats(), sizeof(c), cudaMemcpyDeviceToHost));
   info->last_candidates = static_cast<int64_t>(c[0]);
   info->last_appends = static_cast<int64_t>(c[1]);
@@ -620,6 +682,10 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->mma_wait_epilogue_cycles = static_cast<int64_t>(c[4]);
   info->mma_wait_tma_cycles = static_cast<int64_t>(c[5]);
   info->mma_total_cycles = static_cast<int64_t>(c[6]);
+  for (int i = 0; i < 5; ++i) info->epilogue_cycles[i] = static_cast<int64_t>(c[8 + i]);
+  info->epilogue_cycles[5] = static_cast<int64_t>(c[14]);
+  info->epilogue_cycles[6] = static_cast<int64_t>(c[15]);
+  info->last_wasted_chunks = static_cast<int64_t>(c[13]);
   const double rows = static_cast<double>(h->cfg.n_items);
   info->bytes_fp32 = h->cat_f32 ? rows * h->k_pad * 4.0 : 0.0;
   info->bytes_bf16 = h->cat_bf16 ? rows * h->k_pad * 2.0 : 0.0;

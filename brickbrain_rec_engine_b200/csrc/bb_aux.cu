@@ -239,7 +239,7 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
   {
     WarpMerger mg;
     mg.init(stage_all[warp], lane);
-    const uint32_t thr = __ldcg(P.thr_g + q);
+    const uint32_t thr = thr_load(P, q);
     const int n_slots = P.n_slot_splits * P.n_sub;
     for (int s0 = warp * 32; s0 < n_slots; s0 += 128) {
       const int my_s = s0 + lane;

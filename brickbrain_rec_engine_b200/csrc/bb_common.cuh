@@ -137,7 +137,14 @@ struct ScanParams {
   uint64_t* cand;
   int32_t* cand_cnt;
   int32_t* pub_cnt;       // per slot: number of SORTED keys at the front of the buffer (published at compaction)
-  uint32_t* thr_g;        // per-row shared running threshold (ordered bits), raised by every stream of the row
+  // per-row shared running threshold: (search epoch << 32) | ordered score bits.  Raised (atomicMax) by every stream
+  // of the row on this GPU and -- row-sharded catalogs -- by the other ranks through NVLink peer memory: a rank's
+  // local k'-th best is a valid lower bound of the GLOBAL k'-th best, so every shard may prune with it.  Words of
+  // another epoch (an earlier search, a rank that runs ahead) are ignored by readers and lose every atomicMax.
+  unsigned long long* thr_g;
+  unsigned long long* peer_thr[7];   // the same array on the peer GPUs (cudaIpc mappings)
+  int32_t n_peers;
+  uint32_t epoch;
   // schedule
   int32_t n_qblocks;      // query blocks
   int32_t n_splits;       // catalog splits of the tiles after the pilot (regular units = n_qblocks * n_splits)
@@ -186,6 +193,19 @@ __device__ __forceinline__ UnitInfo decode_unit(const ScanParams& P, int u, int 
   r.split_slot = u / P.n_qblocks;
   split_tile_range(P, r.split_slot, r.t0, r.t1);
   return r;
+}
+
+// ---------------------------------------------------------------- shared threshold words
+__device__ __forceinline__ uint32_t thr_load(const ScanParams& P, int row) {
+  const unsigned long long v = __ldcg(P.thr_g + row);
+  return (static_cast<uint32_t>(v >> 32) == P.epoch) ? static_cast<uint32_t>(v) : kOrdNegInf;
+}
+__device__ __forceinline__ void thr_raise(const ScanParams& P, int row, uint32_t ord) {
+  const unsigned long long v = (static_cast<unsigned long long>(P.epoch) << 32) | ord;
+  atomicMax(P.thr_g + row, v);
+#pragma unroll
+  for (int p = 0; p < 7; ++p)                       // (constant indices: a run-time index would copy the kernel parameters to local memory)
+    if (p < P.n_peers) atomicMax_system(P.peer_thr[p] + row, v);   // fire-and-forget over NVLink
 }
 
 // ---------------------------------------------------------------- hard-constraint predicate
@@ -388,37 +408,55 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
 // buffer could overflow on the next group, publish its sorted prefix, and raise the
 // row's shared threshold (own k'-th best and the cross-stream refinement).
 // `force_mask`: lanes whose buffer is compacted regardless of fill (unit end: leave a sorted, published prefix).
+// `refine_mask`: lanes whose compaction also runs the cross-stream refinement (warp-uniform value).
 // `headroom`: appends a lane may make before the next call (the buffer must not overflow in between).
 __device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane,
-                                                      unsigned force_mask = 0u, bool refine = true, int headroom = 32) {
+                                                      unsigned force_mask = 0u, unsigned refine_mask = kFull, int headroom = 32) {
   __syncwarp();
-  unsigned need = __ballot_sync(kFull, st.cnt > kCap - headroom) | force_mask;
-  const int n_compactions = __popc(need);
-  while (need) {
+  const unsigned need0 = __ballot_sync(kFull, st.cnt > kCap - headroom) | force_mask;
+  if (need0 == 0u) return 0;
+  // phase 1: sort / merge every flagged row's buffer (warp-cooperative, one row at a time)
+  float my_nt = -INFINITY;
+  int my_nc = st.cnt;
+  for (unsigned need = need0; need; need &= need - 1) {
     const int src = __ffs(need) - 1;
-    need &= need - 1;
     uint64_t* b = reinterpret_cast<uint64_t*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(st.buf), src));
     const int c = __shfl_sync(kFull, st.cnt, src);
     const int c_sorted = __shfl_sync(kFull, st.sorted, src);
-    const int src_row = __shfl_sync(kFull, row, src);
-    const long long src_slot = __shfl_sync(kFull, static_cast<long long>(st.slot), src);
     float nt;
     const int nc = warp_compact(b, c, P.k_sel, c_sorted, lane, &nt);
-    __threadfence();                                // sorted keys are visible before the count that advertises them
-    if (lane == 0) atomicMax(P.pub_cnt + src_slot, nc);
-    const uint32_t refined = refine ? warp_refine_threshold(P, src_row, lane) : 0u;
     if (lane == src) {
-      st.cnt = nc;
-      st.sorted = nc;
-      uint32_t o = f2ord(nt);
-      o = refined > o ? refined : o;
-      if (o > f2ord(st.thr)) {
-        st.thr = ord2f(o);
-        atomicMax(P.thr_g + row, o);
-      }
+      my_nt = nt;
+      my_nc = nc;
     }
   }
-  return n_compactions;
+  // phase 2: ONE fence for all rows (sorted keys are visible before the counts that advertise them), then every
+  // flagged lane publishes its own count
+  __threadfence();
+  const bool mine = (need0 >> lane) & 1u;
+  if (mine) {
+    atomicMax(P.pub_cnt + st.slot, my_nc);
+    st.cnt = my_nc;
+    st.sorted = my_nc;
+  }
+  __syncwarp();
+  // phase 3: cross-stream refinement for the rows that asked for it, then raise the shared threshold
+  uint32_t my_ref = 0u;
+  for (unsigned need = need0 & refine_mask; need; need &= need - 1) {
+    const int src = __ffs(need) - 1;
+    const int src_row = __shfl_sync(kFull, row, src);
+    const uint32_t refined = warp_refine_threshold(P, src_row, lane);
+    if (lane == src) my_ref = refined;
+  }
+  if (mine) {
+    uint32_t o = f2ord(my_nt);
+    o = my_ref > o ? my_ref : o;
+    if (o > f2ord(st.thr)) {
+      st.thr = ord2f(o);
+      thr_raise(P, row, o);
+    }
+  }
+  return __popc(need0);
 }
 
 __device__ __forceinline__ void row_append(const ScanParams& P, RowState& st, float score, int64_t item) {

@@ -123,7 +123,7 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
           for (int c = 0; c < XN; ++c)
             if (item0 + c < P.n_items) P.dump[static_cast<int64_t>(own_row) * P.n_items + item0 + c] = sm.s[r][c];
       } else {
-        if (own_row < P.n_queries) st.thr = fmaxf(st.thr, ord2f(__ldcg(P.thr_g + own_row)));
+        if (own_row < P.n_queries) st.thr = fmaxf(st.thr, ord2f(thr_load(P, own_row)));
         for (int g = 0; g < XN / 32; ++g) {
           float4 v[8];
           float m = -INFINITY;

@@ -32,6 +32,18 @@ constexpr int kBlockK = 64;                 // bf16 columns per k-block (= one 1
 constexpr int kAkbBytes = 128 * 128;        // resident query k-block: 128 rows x 128 B
 constexpr int kUmmaK = 16;
 constexpr int kAccCols = kTcTile;           // fp32 accumulator columns per tile
+// Epilogue cycle breakdown (bb_info.epilogue_cycles): compiled in only with -DBB_EPILOGUE_PROFILE=1
+// (BB_EPILOGUE_PROFILE=1 python -m brickbrain_rec_engine_b200.build) -- the clock reads cost ~2% of the scan.
+#ifndef BB_EPILOGUE_PROFILE
+#define BB_EPILOGUE_PROFILE 0
+#endif
+__device__ __forceinline__ long long epi_clock() {
+#if BB_EPILOGUE_PROFILE
+  return clock64();
+#else
+  return 0;
+#endif
+}
 constexpr int kAccStages = 512 / kAccCols;  // TMEM accumulator ring: how far the MMA issuer may run ahead of the epilogue
 constexpr int kTmemCols = 512;              // two accumulators
 constexpr int kEpiWarps = 4 * kTcSubStreams; // kTcSubStreams warps per TMEM lane quarter, each scans a column slice of every tile
@@ -383,7 +395,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t acc_empty_leader_base = (CG == 2) ? mapa_u32(smem_u32(bar_acc_empty), 0) : smem_u32(bar_acc_empty);
     const bool use_cons = kRowCons && P.cons != nullptr && P.class_valid == nullptr;   // per-row prefilter (no class bitmaps)
-    unsigned stat_appends = 0, stat_slow = 0, stat_compact = 0;   // per-thread / per-warp counters (debug statistics)
+    unsigned stat_appends = 0, stat_slow = 0, stat_compact = 0, stat_wasted = 0;   // per-thread / per-warp counters (debug statistics)
+    long long cyc_wait = 0, cyc_slow = 0, cyc_compact = 0, cyc_end = 0, cyc_hold = 0, cyc_ld = 0, t_full = 0;
+    const long long cyc_begin = epi_clock();
     for (int u = group; u < n_units; u += n_groups) {
       const UnitInfo ui = decode_unit(P, u, n_groups);
       if (!ui.valid) continue;
@@ -429,13 +443,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       st.slot = slot;
       int next_pub = 32;                             // early-publish schedule of a cold stream
       const bool share_thr = !dead && P.dump == nullptr;
-      uint32_t thr_next = share_thr ? __ldcg(P.thr_g + q) : 0u;   // shared threshold, fetched one tile ahead
+      uint32_t thr_next = share_thr ? thr_load(P, q) : kOrdNegInf;   // shared threshold, fetched one tile ahead
       for (int t = t0; t < t1; ++t) {
         if (share_thr) {
           st.thr = fmaxf(st.thr, ord2f(thr_next));
-          thr_next = __ldcg(P.thr_g + q);
+          thr_next = thr_load(P, q);
         }
-        mbar_wait<true>(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
+        {
+          const long long c0 = epi_clock();
+          mbar_wait<true>(smem_u32(bar_acc_full + acc), acc_phase, err, 106);
+          t_full = epi_clock();
+          cyc_wait += t_full - c0;
+        }
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * kAccCols;
         const int64_t item0 = static_cast<int64_t>(t) * kTcTile;
@@ -453,6 +472,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             continue;
           }
           uint32_t r[32];
+          const long long t_ld = epi_clock();
           tmem_ld32(taddr + chunk * 32, r);
           // this lane also "owns" one column of the chunk: fetch and unpack its metadata while the TMEM load is
           // in flight (only batches with per-row constraints pay for it)
@@ -470,6 +490,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             cm.w = (c_theme >= 0 && c_theme < 1024) ? (1u << (c_theme & 31)) : 0u;                  // theme bit (0 = NULL)
           }
           tmem_ld_wait();
+          cyc_ld += epi_clock() - t_ld;
+          if (chunk == (half + 1) * kChunksPerWarp - 1) cyc_hold += epi_clock() - t_full;
           if (chunk == (half + 1) * kChunksPerWarp - 1) {
             // the tile's last slice is in registers: hand the accumulator back to the MMA issuer BEFORE
             // processing it, so slow-path work and compactions overlap the next tile's MMAs
@@ -490,23 +512,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             continue;
           }
-          float m = __uint_as_float(r[0]);
+          // per row: the columns whose score passes the row's threshold and whose item the row's constraint set
+          // admits (class mode: one prefetched bitmap word masks the 32 columns; a passing score of a masked-out
+          // item must not drag the warp into the slow path -- two thirds of the triggers were of that kind)
+          unsigned pm = 0;
 #pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-          // (class mode: a row whose constraint set admits none of this chunk's 32 items cannot have a candidate,
-          //  whatever its scores -- selective rows then stop dragging their warp into the slow path)
-          if (__any_sync(kFull, m >= st.thr && class_word != 0u) && !(P.debug_flags & 1)) {
-            // ---- slow path, entered only when some row of this warp has a score >= its threshold
+          for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= st.thr) ? (1u << j) : 0u;
+          pm &= ~__ballot_sync(kFull, col_item >= P.n_items);
+          if (!(P.debug_flags & 128)) pm &= class_word;      // (flag 128: A/B switch, trigger on unmasked scores)
+          if (__any_sync(kFull, pm != 0u) && !(P.debug_flags & 1)) {
+            // ---- slow path, entered only when some row of this warp has a live candidate
             ++stat_slow;
-            unsigned pm = 0;                                   // per row: columns whose score passes
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= st.thr) ? (1u << j) : 0u;
-            pm &= ~__ballot_sync(kFull, col_item >= P.n_items);
-            if (P.class_valid != nullptr) {
-              // few distinct constraint sets in the batch: their validity bitmaps were built by the mask kernel,
-              // one prefetched word masks this row's 32 columns
-              pm &= class_word;
-            } else if (use_cons) {
+            const long long c0 = epi_clock();
+            pm &= class_word;
+            if (use_cons) {
               // column owners publish their item's unpacked metadata (prefetched above) in shared memory;
               // every row then checks only ITS OWN passing columns (trip count = max passes of one row)
               __syncwarp();
@@ -524,8 +543,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
               pm = vm;
               __syncwarp();
             }
-            if (__any_sync(kFull, pm != 0u)) {
-              // ---- rare: a masked-in candidate exists
+            if (!__any_sync(kFull, pm != 0u)) ++stat_wasted;
+            else {
+              // ---- a masked-in candidate exists
               while (__any_sync(kFull, pm != 0u)) {
                 if (pm != 0u) {
                   const int j = __ffs(pm) - 1;
@@ -550,18 +570,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 }
               }
             }
+            cyc_slow += epi_clock() - c0;
           }
         }
         // deferred compaction (after the accumulator was released): a tile appends at most 32 keys per chunk
         if (P.dump == nullptr && !(P.debug_flags & 3)) {
-          // cold streams (no threshold yet) publish a small sorted prefix early: the row's concurrently cold
-          // streams then find a shared threshold after ~32 candidates each instead of ~200 each
-          const bool pub_now = !dead && st.thr == -INFINITY && st.cnt >= next_pub;
+          // (only with in-scan refinement switched on, debug flags 16 / 32: cold streams publish a small sorted
+          //  prefix early so that the row's concurrently cold streams can find a shared threshold sooner)
+          const bool pub_now = !dead && st.thr == -INFINITY && st.cnt >= next_pub && (P.debug_flags & (16 | 32)) != 0;
           if (pub_now) next_pub *= 2;                // 32, 64, 128, then only the regular overflow trigger
           const unsigned early = __ballot_sync(kFull, pub_now);
           // (in-scan compactions only publish; measured: refining here costs more stall than the tighter threshold saves --
           //  the refinement at unit end is what keeps later units warm)
-          stat_compact += warp_compact_if_needed(P, st, q, lane, early, (P.debug_flags & 16) != 0, 32 * kChunksPerWarp);
+          const long long c0 = epi_clock();
+          const int nc = warp_compact_if_needed(P, st, q, lane, early, (P.debug_flags & 16) ? kFull : ((P.debug_flags & 32) ? early : 0u), 32 * kChunksPerWarp);
+          stat_compact += nc;
+          if (nc) cyc_compact += epi_clock() - c0;
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
@@ -571,7 +595,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
         const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt >= 8);
         // (one of the row's column-slice streams refines; the others only sort + publish)
-        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, half == 0 && !(P.debug_flags & 8));
+        const long long c0 = epi_clock();
+        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, (half == 0 && !(P.debug_flags & 8)) ? kFull : 0u);
+        cyc_end += epi_clock() - c0;
         P.cand_cnt[slot] = st.cnt;
         if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
       }
@@ -582,6 +608,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         atomicAdd(P.stat_candidates + 1, static_cast<unsigned long long>(a));
         atomicAdd(P.stat_candidates + 2, static_cast<unsigned long long>(stat_slow));
         atomicAdd(P.stat_candidates + 3, static_cast<unsigned long long>(stat_compact));
+        atomicAdd(P.stat_candidates + 13, static_cast<unsigned long long>(stat_wasted));
+        atomicAdd(P.stat_candidates + 14, static_cast<unsigned long long>(cyc_hold));
+        atomicAdd(P.stat_candidates + 15, static_cast<unsigned long long>(cyc_ld));
+        atomicAdd(P.stat_candidates + 8, static_cast<unsigned long long>(cyc_wait));
+        atomicAdd(P.stat_candidates + 9, static_cast<unsigned long long>(cyc_slow));
+        atomicAdd(P.stat_candidates + 10, static_cast<unsigned long long>(cyc_compact));
+        atomicAdd(P.stat_candidates + 11, static_cast<unsigned long long>(cyc_end));
+        atomicAdd(P.stat_candidates + 12, static_cast<unsigned long long>(epi_clock() - cyc_begin));
       }
     }
   }

@@ -119,11 +119,24 @@ class ScoringEngine:
         i = L.bb_info()
         i.struct_size = C.sizeof(L.bb_info)
         self._check(self._lib.bb_get_info(self._h, C.byref(i)))
-        return {f: getattr(i, f) for f, _ in L.bb_info._fields_ if f != "struct_size"}
+        d = {f: getattr(i, f) for f, _ in L.bb_info._fields_ if f != "struct_size"}
+        d["epilogue_cycles"] = list(d["epilogue_cycles"])
+        return d
 
     def set_profiling(self, enable: bool = True):
         """Bracket every scan launch with CUDA events; totals appear in ``info()['scan_ms']``."""
         self._check(self._lib.bb_set_profiling(self._h, 1 if enable else 0))
+
+    def export_threshold_handle(self) -> bytes:
+        """cudaIpc handle of this shard's per-query threshold array (row-sharded catalogs, see ShardedSearch)."""
+        buf = C.create_string_buffer(L.BB_IPC_HANDLE_BYTES)
+        self._check(self._lib.bb_export_threshold_handle(self._h, buf))
+        return buf.raw
+
+    def import_peer_thresholds(self, handles: Sequence[bytes]):
+        """Maps the threshold arrays of the OTHER ranks; the scan then raises them through NVLink peer memory."""
+        blob = b"".join(handles)
+        self._check(self._lib.bb_import_peer_thresholds(self._h, len(handles), C.c_char_p(blob) if handles else None))
 
     @property
     def launches(self) -> int:
@@ -241,12 +254,15 @@ class ScoringEngine:
 
     def search(self, k: int, q_emb=None, q_item=None, q_cf=None, w_content=1.0, w_cf=0.0, constraints=None,
                self_id=None, precision: str = "fp32", as_l2: bool = False, out=None, stream=None,
-               constraint_index=None) -> Tuple[object, object]:
+               constraint_index=None, share_thresholds: bool = False) -> Tuple[object, object]:
         """Fused score + blend + mask + top-k.  Returns (scores[B,k] float32, ids[B,k] int32).
-        Outputs are CUDA tensors when any input is a CUDA tensor (or ``out`` is given), else NumPy."""
+        Outputs are CUDA tensors when any input is a CUDA tensor (or ``out`` is given), else NumPy.
+        ``share_thresholds`` marks a collective search of a row-sharded catalog (``ShardedSearch``)."""
         a = _Args()
         qb, b = self._batch(a, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2,
                             constraint_index)
+        if share_thresholds:
+            qb.flags |= L.BB_Q_SHARE_THRESHOLDS
         if out is not None:
             scores, ids = out
             ps, pi = a.ptr(scores, np.float32, (b, k)), a.ptr(ids, np.int32, (b, k))

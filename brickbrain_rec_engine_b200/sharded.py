@@ -28,20 +28,50 @@ def shard_bounds(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def exchange_threshold_handles(engine, group=None) -> bool:
+    """All ranks export the cudaIpc handle of their per-query threshold array and map everyone else's, so the
+    scan kernels of all shards raise ONE logical threshold per query through NVLink peer memory (a rank's local
+    k-th best is a valid lower bound of the global k-th best).  Returns False when the engine was created without
+    max_batch (no exportable array) -- sharding still works, each shard then prunes on its own."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    try:
+        mine = engine.export_threshold_handle()
+    except Exception:
+        mine = None
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    if any(h is None for h in handles):
+        return False
+    engine.import_peer_thresholds([h for r, h in enumerate(handles) if r != rank])
+    return True
+
+
 class ShardedSearch:
     """Couples a per-rank engine (anything with ``search`` and ``merge_topk``) with the
     candidate all-gather.  ``engine.id_offset`` must equal this rank's ``shard_bounds`` begin."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, share_thresholds: bool = True):
         if dist is None or not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialized (one process per GPU)")
         self.engine = engine
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.shared = False
+        if share_thresholds and self.world_size > 1 and hasattr(engine, "export_threshold_handle"):
+            self.shared = exchange_threshold_handles(engine, group)
 
     def search(self, k: int, **kwargs):
         """Same keyword arguments as ``ScoringEngine.search``; returns the GLOBAL top-k on every rank."""
+        if self.shared:
+            kwargs["share_thresholds"] = True
+        # host (NumPy) callers over an NCCL group: the per-shard result stays on the device for the gather + merge
+        on_device = (self.world_size > 1 and kwargs.get("out") is None and dist.get_backend(self.group) == "nccl"
+                     and not any(torch.is_tensor(v) and v.is_cuda for v in kwargs.values()))
+        if on_device:
+            b = next(len(kwargs[n]) for n in ("q_emb", "q_item", "q_cf") if kwargs.get(n) is not None)
+            dev = f"cuda:{self.engine.device}"
+            kwargs["out"] = (torch.empty((b, k), dtype=torch.float32, device=dev), torch.empty((b, k), dtype=torch.int32, device=dev))
         scores, ids = self.engine.search(k, **kwargs)
         if self.world_size == 1:
             return scores, ids
@@ -54,5 +84,6 @@ class ShardedSearch:
         dist.all_gather_into_tensor(all_s.view(-1), s_t.reshape(-1).contiguous(), group=self.group)
         dist.all_gather_into_tensor(all_i.view(-1), i_t.reshape(-1).contiguous(), group=self.group)
         if as_torch:
-            return self.engine.merge_topk(all_s, all_i, k)
+            ms, mi = self.engine.merge_topk(all_s, all_i, k)
+            return (ms.cpu().numpy(), mi.cpu().numpy()) if on_device else (ms, mi)
         return self.engine.merge_topk(all_s.numpy(), all_i.numpy(), k)

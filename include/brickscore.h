@@ -59,6 +59,7 @@ extern "C" {
 
 /* bb_query_batch.flags */
 #define BB_Q_SCORES_AS_L2 1u /* report 2 - 2*score (FAISS IndexFlatL2 distance on unit vectors) */
+#define BB_Q_SHARE_THRESHOLDS 2u /* collective search of a row-sharded catalog, see bb_import_peer_thresholds */
 
 /* bb_constraint.flags */
 #define BB_C_ALWAYS_FALSE 1u /* THEMES_REQUIRED matched no theme: "1=0" (hard_constraint_filter.py:408-409) */
@@ -132,6 +133,11 @@ typedef struct bb_info {
   double bytes_fp32, bytes_bf16; /* resident operand bytes */
   double scan_ms;           /* device time of the scan kernels since bb_set_profiling(h, 1) (CUDA events) */
   int64_t scan_launches;    /* scan kernel launches covered by scan_ms */
+  /* sum over epilogue warps of the last scan, in cycles: [0] waiting for a full accumulator, [1] slow path
+   * (threshold passed: mask + append), [2] in-scan compactions, [3] unit-end compaction + refine, [4] total,
+   * [5] accumulator hold (full -> released), [6] TMEM loads (issue -> data in registers) */
+  int64_t epilogue_cycles[7];
+  int64_t last_wasted_chunks; /* slow-path chunks whose passing scores were all masked out (no append) */
 } bb_info;
 
 BB_API const char* bb_version(void);
@@ -216,6 +222,21 @@ BB_API int bb_merge_topk(bb_handle* h, int32_t n_queries, int32_t n_lists, int32
  */
 BB_API int bb_item_item_topk(bb_handle* h, int64_t n_users, int32_t n_items, const int64_t* indptr, const int32_t* indices,
                       const float* values, int32_t k, float* out_scores, int32_t* out_ids, void* stream);
+
+/*
+ * Row-sharded catalogs (one process per GPU): the per-query running thresholds of the scan can be shared between
+ * the ranks through NVLink peer memory, so that every shard prunes with the best bound any shard has found (a
+ * rank's local k-th best is a valid lower bound of the global k-th best).  Each rank exports the handle of its
+ * threshold array (requires bb_config.max_batch > 0), the ranks exchange the 64-byte handles (e.g. all-gather) and
+ * import the other ranks' handles (a collective: every rank imports before any rank searches again).  Searches
+ * flagged BB_Q_SHARE_THRESHOLDS are then collective too: all ranks issue the same sequence of them with the same
+ * replicated query batch, one at a time.  The merged result is unchanged; a rank's own output may hold fewer than
+ * k entries (-1 padded), since items that cannot reach the global top-k are pruned early.  Unflagged searches are
+ * unaffected.
+ */
+#define BB_IPC_HANDLE_BYTES 64
+BB_API int bb_export_threshold_handle(bb_handle* h, void* out_handle);
+BB_API int bb_import_peer_thresholds(bb_handle* h, int32_t n_peers, const void* handles);
 
 /* Test / diagnosis aid: dense score matrix [B x n_items] from the selected scan pipeline. */
 BB_API int bb_debug_scores(bb_handle* h, const bb_query_batch* q, float* out_scores, void* stream);

@@ -16,6 +16,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared object is git-ignored: build it when a fresh checkout runs the suite before __graft_entry__.build()
+    lib = os.path.join(ROOT, "brickbrain_rec_engine_b200", "libbrickscore.so")
+    if not os.path.exists(lib):
+        from brickbrain_rec_engine_b200 import build as _b
+        _b.build()
 
 
 @pytest.fixture(scope="session")

@@ -472,3 +472,19 @@ def test_reentrant_two_streams(bb):
     for t in range(2):
         assert np.array_equal(got[t][1], want[t][1]) and np.array_equal(got[t][0], want[t][0])
     eng.close()
+
+
+def test_sharded_search_two_gpus():
+    """Row-sharded catalog on 2 GPUs (NCCL all-gather + merge, thresholds shared through NVLink peer memory) returns
+    exactly what one engine over the whole catalog returns (tools/shard_check.py).  Needs a 2-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SC_N="200000", SC_B="512")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "shard_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0 and "SHARD_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
