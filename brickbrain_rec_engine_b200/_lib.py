@@ -85,7 +85,8 @@ class bb_info(C.Structure):
                 ("last_candidates", C.c_int64), ("last_appends", C.c_int64), ("last_slow_chunks", C.c_int64),
                 ("last_compactions", C.c_int64), ("mma_wait_epilogue_cycles", C.c_int64),
                 ("mma_wait_tma_cycles", C.c_int64), ("mma_total_cycles", C.c_int64), ("bytes_fp32", C.c_double), ("bytes_bf16", C.c_double),
-                ("scan_ms", C.c_double), ("scan_launches", C.c_int64), ("epilogue_cycles", C.c_int64 * 7), ("last_wasted_chunks", C.c_int64)]
+                ("scan_ms", C.c_double), ("scan_launches", C.c_int64), ("epilogue_cycles", C.c_int64 * 7), ("round_cycles", C.c_int64 * 16), ("round_wait_cycles", C.c_int64 * 16),
+                ("last_wasted_chunks", C.c_int64)]
 
 
 #: every symbol include/brickscore.h declares: name -> (restype, argtypes)
@@ -109,6 +110,7 @@ PROTOTYPES = {
     "bb_merge_topk": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "bb_item_item_topk": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "bb_debug_scores": (C.c_int, [_P, C.POINTER(bb_query_batch), _P, _P]),
+    "bb_csr_spmm_f64": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "bb_export_threshold_handle": (C.c_int, [_P, _P]),
     "bb_import_peer_thresholds": (C.c_int, [_P, C.c_int32, _P]),
 }

@@ -186,7 +186,7 @@ Workspace* get_ws(bb_handle* h, cudaStream_t s) {
     cudaGetLastError();
     w->host_flag = nullptr;
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&w->ctl), 256) != cudaSuccess || cudaMemset(w->ctl, 0, 256) != cudaSuccess) {
+  if (cudaMalloc(reinterpret_cast<void**>(&w->ctl), 1024) != cudaSuccess || cudaMemset(w->ctl, 0, 1024) != cudaSuccess) {
     cudaGetLastError();
     if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
     delete w;
@@ -453,6 +453,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     }
     P.wave_counter = w->wave_counter();
     BB_CUDA(h, cudaMemsetAsync(w->ctl, 0, 192, stream));
+    BB_CUDA(h, cudaMemsetAsync(w->ctl + 256, 0, 256, stream));
   }
 
   // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
@@ -686,6 +687,14 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->epilogue_cycles[5] = static_cast<int64_t>(c[14]);
   info->epilogue_cycles[6] = static_cast<int64_t>(c[15]);
   info->last_wasted_chunks = static_cast<int64_t>(c[13]);
+  {
+    unsigned long long r[32] = {0};
+    if (h->last_ws != nullptr) BB_CUDA(h, cudaMemcpy(r, h->last_ws->stats() + 32, sizeof(r), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) {
+      info->round_cycles[i] = static_cast<int64_t>(r[i]);
+      info->round_wait_cycles[i] = static_cast<int64_t>(r[16 + i]);
+    }
+  }
   const double rows = static_cast<double>(h->cfg.n_items);
   info->bytes_fp32 = h->cat_f32 ? rows * h->k_pad * 4.0 : 0.0;
   info->bytes_bf16 = h->cat_bf16 ? rows * h->k_pad * 2.0 : 0.0;
@@ -1050,6 +1059,22 @@ int bb_merge_topk(bb_handle* h, int32_t n_queries, int32_t n_lists, int32_t len,
   if (!s_dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d_s, 4 * n_out, cudaMemcpyDeviceToHost, stream));
   if (!i_dev) BB_CUDA(h, cudaMemcpyAsync(out_ids, d_i, 4 * n_out, cudaMemcpyDeviceToHost, stream));
   if (!s_dev || !i_dev) BB_CUDA(h, cudaStreamSynchronize(stream));
+  return BB_OK;
+}
+
+int bb_csr_spmm_f64(bb_handle* h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                    const float* values, const double* x, int32_t l, double* y, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (n_rows <= 0 || n_cols <= 0 || l <= 0 || l > 128) return fail(h, BB_ERR_INVALID, "csr_spmm: bad shape (L must be in [1, 128])");
+  if (indptr == nullptr || indices == nullptr || values == nullptr || x == nullptr || y == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  if (!is_device_ptr(indptr) || !is_device_ptr(indices) || !is_device_ptr(values) || !is_device_ptr(x) || !is_device_ptr(y))
+    return fail(h, BB_ERR_INVALID, "csr_spmm: all arrays must be device pointers");
+  if (nnz <= 0) return fail(h, BB_ERR_INVALID, "csr_spmm: nnz must be positive");
+  BB_CUDA(h, launch_csr_spmm_f64(n_rows, nnz, indptr, indices, values, x, l, y, h->sm_count, stream));
+  h->launches += 2;
   return BB_OK;
 }
 

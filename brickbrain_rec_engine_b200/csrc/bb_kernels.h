@@ -34,6 +34,9 @@ cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const
 cudaError_t launch_pack_meta(const int32_t* num_parts, const int16_t* year, const int16_t* theme, int64_t n_rows,
                              int2* out, cudaStream_t stream);
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream);
+// Y[n_rows x L] = CSR(n_rows x *) * X[* x L], fp32 values, fp64 X / Y (bb_spmm.cu); L <= 128
+cudaError_t launch_csr_spmm_f64(int64_t n_rows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const float* values,
+                                const double* X, int L, double* Y, int sm_count, cudaStream_t stream);
 cudaError_t launch_gather_rows(const float* cat_f32, const void* cat_bf16, int k_pad, int dim, int64_t id_offset,
                                int64_t n_items, const int32_t* ids, int n, float* out, int32_t* err_flag,
                                cudaStream_t stream);

@@ -345,8 +345,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const UnitInfo ui = decode_unit(P, u, n_groups);
         if (!ui.valid) continue;
         const int t0 = ui.t0, t1 = ui.t1;
+        const long long tu0 = epi_clock();
         mbar_wait(smem_u32(bar_a_full), a_phase, err, 103);
         a_phase ^= 1;
+        const long long tu1 = epi_clock();
         for (int t = t0; t < t1; ++t) {
           long long tw = clock64();
           mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1, err, 104);
@@ -378,6 +380,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         if (lane == 0) umma_commit<CG>(smem_u32(bar_a_empty));            // query operand no longer read
         __syncwarp();
+#if BB_EPILOGUE_PROFILE
+        if (lane == 0 && P.stat_candidates != nullptr) {      // per scheduling round: unit duration and its operand wait
+          const int round = min((u - group) / n_groups, 15);
+          atomicAdd(P.stat_candidates + 32 + round, static_cast<unsigned long long>(clock64() - tu0));
+          atomicAdd(P.stat_candidates + 48 + round, static_cast<unsigned long long>(tu1 - tu0));
+        }
+#endif
       }
       if (lane == 0 && P.stat_candidates != nullptr) {
         atomicAdd(P.stat_candidates + 4, static_cast<unsigned long long>(t_acc_wait));

@@ -120,7 +120,8 @@ class ScoringEngine:
         i.struct_size = C.sizeof(L.bb_info)
         self._check(self._lib.bb_get_info(self._h, C.byref(i)))
         d = {f: getattr(i, f) for f, _ in L.bb_info._fields_ if f != "struct_size"}
-        d["epilogue_cycles"] = list(d["epilogue_cycles"])
+        for f in ("epilogue_cycles", "round_cycles", "round_wait_cycles"):
+            d[f] = list(d[f])
         return d
 
     def set_profiling(self, enable: bool = True):
@@ -335,6 +336,23 @@ class ScoringEngine:
             po_s, po_i = out_s.ctypes.data, out_i.ctypes.data
         self._check(self._lib.bb_merge_topk(self._h, b, n_lists, ln, ps, pi, k, po_s, po_i, self._stream(stream)))
         return out_s, out_i
+
+    def csr_spmm(self, indptr, indices, values, n_cols: int, x, out=None, stream=None):
+        """``Y = A @ x`` for a CSR matrix ``A`` (int64 indptr, int32 indices, float32 values) and a dense float64
+        ``x`` [n_cols, L]; all CUDA tensors on this engine's device.  The sparse products of ``cf_training``."""
+        for t, dt in ((indptr, torch.int64), (indices, torch.int32), (values, torch.float32), (x, torch.float64)):
+            if not (torch.is_tensor(t) and t.is_cuda and t.dtype == dt and t.is_contiguous()):
+                raise ValueError("csr_spmm expects contiguous CUDA tensors: int64 indptr, int32 indices, float32 values, float64 x")
+        n_rows, l = int(indptr.shape[0]) - 1, int(x.shape[1])
+        if int(x.shape[0]) != n_cols:
+            raise ValueError("x must have n_cols rows")
+        if out is None:
+            out = torch.empty((n_rows, l), dtype=torch.float64, device=x.device)
+        if indices.numel() == 0:                       # no stored entries: the product is zero
+            return out.zero_()
+        self._check(self._lib.bb_csr_spmm_f64(self._h, n_rows, n_cols, int(indices.numel()), indptr.data_ptr(), indices.data_ptr(), values.data_ptr(),
+                                              x.data_ptr(), l, out.data_ptr(), self._stream(stream)))
+        return out
 
     def item_item_topk(self, indptr, indices, values, n_items: int, k: int):
         """Item-item cosine top-k from a user x item CSR rating matrix (BASELINE config 3)."""

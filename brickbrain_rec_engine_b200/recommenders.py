@@ -210,8 +210,27 @@ class CollaborativeFilteringRecommender:
         self.precision = precision
 
     def train_svd_model(self, n_components: int = 50):
-        logger.warning("SVD training (recommendation_system.py:368-409) is out of scope; no factors injected")
-        self.svd_model = None
+        """recommendation_system.py:368-409 on the GPU (``cf_training.truncated_svd``): same guards, same factors.
+        Needs ``self.user_item_matrix`` (users x catalog rows, 0 = unrated; ndarray, DataFrame or scipy sparse)."""
+        from .cf_training import truncated_svd
+        m = getattr(self, "user_item_matrix", None)
+        if m is None:
+            logger.warning("train_svd_model: no user_item_matrix injected")
+            self.svd_model = None
+            return
+        m = m.values if hasattr(m, "values") else m
+        if m.shape[0] < 3 or m.shape[1] < 3:
+            logger.warning(f"Insufficient data for SVD: {m.shape}. Need at least 3 users and 3 items.")
+            self.svd_model = None
+            return
+        n_components = min(n_components, min(m.shape) - 1)
+        if n_components < 2:
+            logger.warning("Not enough components for SVD, using fallback recommendations")
+            self.svd_model = None
+            return
+        self.user_factors, self.item_factors, _ = truncated_svd(self.engine, m, n_components)
+        self.svd_model = object()
+        logger.info(f"Trained SVD model with {n_components} components")
 
     def get_recommendations(self, user_id, top_k: int = 10,
                             valid_set_filter: Optional[List[str]] = None) -> List[RecommendationResult]:

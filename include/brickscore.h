@@ -137,6 +137,10 @@ typedef struct bb_info {
    * (threshold passed: mask + append), [2] in-scan compactions, [3] unit-end compaction + refine, [4] total,
    * [5] accumulator hold (full -> released), [6] TMEM loads (issue -> data in registers) */
   int64_t epilogue_cycles[7];
+  /* (profiling build) per scheduling round of the last scan, summed over CTA pairs: unit duration and the part of
+   * it spent waiting for the query operand (includes the wave barrier); rounds >= 15 share the last bucket */
+  int64_t round_cycles[16];
+  int64_t round_wait_cycles[16];
   int64_t last_wasted_chunks; /* slow-path chunks whose passing scores were all masked out (no append) */
 } bb_info;
 
@@ -237,6 +241,16 @@ BB_API int bb_item_item_topk(bb_handle* h, int64_t n_users, int32_t n_items, con
 #define BB_IPC_HANDLE_BYTES 64
 BB_API int bb_export_threshold_handle(bb_handle* h, void* out_handle);
 BB_API int bb_import_peer_thresholds(bb_handle* h, int32_t n_peers, const void* handles);
+
+/*
+ * Sparse (CSR ratings, fp32 values) x dense (fp64, row-major) product, Y[n_rows x L] = A[n_rows x n_cols] * X[n_cols x L]:
+ * the A @ Q, A.T @ Q (pass the CSR of A.T) and A @ V products of the randomized truncated SVD that trains the
+ * collaborative-filtering factors (reference: recommendation_system.py:368-409, sklearn TruncatedSVD).  L <= 128.
+ * All pointers are DEVICE pointers (the training loop keeps its matrices resident).  Rows with more than 2048
+ * entries are summed with fp64 atomics (last-bit run-to-run differences); shorter rows are deterministic.
+ */
+BB_API int bb_csr_spmm_f64(bb_handle* h, int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                           const float* values, const double* x, int32_t l, double* y, void* cuda_stream);
 
 /* Test / diagnosis aid: dense score matrix [B x n_items] from the selected scan pipeline. */
 BB_API int bb_debug_scores(bb_handle* h, const bb_query_batch* q, float* out_scores, void* stream);

@@ -415,6 +415,41 @@ def item_item_topk(indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, n_
 # CPU baselines for bench.py (timed, never the product path)
 # --------------------------------------------------------------------------------------
 
+def truncated_svd_factors(ratings: np.ndarray, n_components: int = 50, n_iter: int = 5, n_oversamples: int = 10,
+                          random_state: int = 42) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """CF factor training: ``train_svd_model`` (recommendation_system.py:368-409) =
+    ``TruncatedSVD(n_components, random_state=42).fit_transform(user_item_matrix)`` and ``components_.T``
+    (recommendation_system.py:399-407).  The arithmetic is scikit-learn's (third-party, not under the reference
+    tree; 1.9.0 here, reference pin >= 1.3): ``sklearn.utils.extmath._randomized_svd`` with the TruncatedSVD
+    defaults (algorithm="randomized", n_iter=5, n_oversamples=10, power_iteration_normalizer="auto" -> LU,
+    transpose="auto"), ``svd_flip(u_based_decision=False)``, ``X_transformed = X @ components_.T``.
+    Pinned: reproduces the factors the reference produced for tests/golden/cf_golden.npz bit for bit.
+    Returns (user_factors [U, F], item_factors [N, F], singular_values [F])."""
+    from scipy import linalg
+    m = np.asarray(ratings, dtype=np.float64)
+    rs = np.random.RandomState(random_state)
+    n_random = n_components + n_oversamples
+    transpose = m.shape[0] < m.shape[1]
+    w = m.T if transpose else m
+    q = rs.normal(size=(w.shape[1], n_random))
+    for _ in range(n_iter):
+        q, _ = linalg.lu(w @ q, permute_l=True, check_finite=False)
+        q, _ = linalg.lu(w.T @ q, permute_l=True, check_finite=False)
+    q, _ = linalg.qr(w @ q, mode="economic", check_finite=False)
+    b = q.T @ w
+    uhat, s, vt = linalg.svd(b, full_matrices=False, lapack_driver="gesdd")
+    u = q @ uhat
+    if transpose:
+        vt_f, s_f = u[:, :n_components].T.copy(), s[:n_components]
+    else:
+        vt_f, s_f = vt[:n_components].copy(), s[:n_components]
+    idx = np.argmax(np.abs(vt_f), axis=1)
+    sign = np.sign(vt_f[np.arange(vt_f.shape[0]), idx])
+    sign[sign == 0] = 1.0
+    vt_f *= sign[:, None]
+    return m @ vt_f.T, vt_f.T.copy(), s_f
+
+
 def reference_style_query(q_emb: np.ndarray, q_cf: np.ndarray, emb: np.ndarray, item_factors: np.ndarray,
                           valid_ids: Optional[set], w_c: float, w_f: float, top_k: int):
     """One query the way the reference executes it (no batch API): per-query

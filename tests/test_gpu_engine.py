@@ -488,3 +488,58 @@ def test_sharded_search_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "shard_check.py")],
                        capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert r.returncode == 0 and "SHARD_CHECK OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# CF factor training: CSR x dense fp64 kernel + the randomized truncated SVD around it
+# ---------------------------------------------------------------------------------------------
+def test_csr_spmm_matches_scipy(bb):
+    import scipy.sparse as sp
+    import torch
+    rng = np.random.default_rng(11)
+    eng = bb.ScoringEngine(64, 64, 0)
+    for (r, c, dens, l) in ((500, 300, 0.05, 60), (64, 1536, 0.02, 17), (3000, 40, 0.9, 128), (5, 7, 0.0, 33)):
+        a = sp.random(r, c, density=dens, format="csr", random_state=7, dtype=np.float32,
+                      data_rvs=lambda n: rng.integers(1, 6, n).astype(np.float32))
+        if r == 3000:                                  # one very long row (> the long-row kernel's threshold)
+            a = sp.vstack([a, sp.csr_matrix(np.tile(rng.integers(1, 6, c).astype(np.float32), (1, 1)))]).tocsr()
+            a = sp.hstack([a] * 70).tocsr()            # 2800 columns, dense rows of ~2500 entries
+        a.sort_indices()
+        x = rng.standard_normal((a.shape[1], l))
+        y = eng.csr_spmm(torch.from_numpy(a.indptr.astype(np.int64)).cuda(), torch.from_numpy(a.indices.astype(np.int32)).cuda(),
+                         torch.from_numpy(a.data.astype(np.float32)).cuda(), a.shape[1], torch.from_numpy(x).cuda())
+        ref = a.astype(np.float64) @ x
+        np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+    with pytest.raises(Exception):
+        eng.csr_spmm(torch.zeros(3, dtype=torch.int64).cuda(), torch.zeros(1, dtype=torch.int32).cuda(),
+                     torch.zeros(1, dtype=torch.float32).cuda(), 4, torch.zeros((4, 200), dtype=torch.float64).cuda())   # L > 128
+    eng.close()
+
+
+def test_svd_training_matches_reference_factors(bb, golden_dir):
+    """train_svd_model on the GPU vs the factors the unmodified reference trained (cf_golden.npz, TruncatedSVD
+    random_state=42) and vs the oracle on a tall matrix; fp64 arithmetic, bar 1e-8 absolute on factors of O(10)."""
+    from brickbrain_rec_engine_b200 import cf_training
+    g = _golden(golden_dir, "cf_golden.npz")
+    ratings = g["ratings"].astype(np.float32)
+    eng = bb.ScoringEngine(64, 64, 0)
+    uf, itf, s = cf_training.truncated_svd(eng, ratings, g["user_factors"].shape[1])
+    np.testing.assert_allclose(uf, g["user_factors"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(itf, g["item_factors"], rtol=0, atol=1e-9)
+    rng = np.random.default_rng(5)
+    tall = ((rng.random((4000, 600)) < 0.03) * rng.integers(1, 6, (4000, 600))).astype(np.float32)
+    ouf, oitf, os_ = bo.truncated_svd_factors(tall, 50)
+    uf2, itf2, s2 = cf_training.truncated_svd(eng, tall, 50)
+    np.testing.assert_allclose(s2, os_, rtol=1e-10)
+    np.testing.assert_allclose(uf2 @ itf2.T, ouf @ oitf.T, rtol=0, atol=1e-8)       # what scoring consumes
+    np.testing.assert_allclose(itf2, oitf, rtol=0, atol=1e-7)
+    # recommender seam: same guards as recommendation_system.py:381-396
+    cf = bb.CollaborativeFilteringRecommender(engine=eng)
+    cf.user_item_matrix = ratings
+    cf.train_svd_model(50)
+    assert cf.svd_model is not None
+    np.testing.assert_allclose(cf.item_factors, g["item_factors"], rtol=0, atol=1e-9)
+    cf.user_item_matrix = ratings[:2]
+    cf.train_svd_model(50)
+    assert cf.svd_model is None
+    eng.close()

@@ -148,3 +148,22 @@ def test_hybrid_end_to_end(golden_dir):
         ref_ids = np.array(case["ids"])
         ref_sc = np.array([np.nan if s is None else s for s in case["scores"]])
         _assert_ranked_equal(ref_ids, ref_sc, np.asarray(ids), np.asarray(sc), rtol=2e-6, what=str(case["kwargs"]))
+
+
+def test_svd_training_oracle_reproduces_reference_factors(golden_dir):
+    """truncated_svd_factors vs the factors the reference's train_svd_model produced (make_golden.py, cf_golden.npz)
+    and vs scikit-learn's TruncatedSVD run here."""
+    g = np.load(os.path.join(golden_dir, "cf_golden.npz"), allow_pickle=False)
+    ratings = g["ratings"].astype(np.float64)
+    uf, itf, s = bo.truncated_svd_factors(ratings, g["user_factors"].shape[1])
+    np.testing.assert_allclose(uf, g["user_factors"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(itf, g["item_factors"], rtol=0, atol=1e-12)
+    from sklearn.decomposition import TruncatedSVD
+    rng = np.random.default_rng(3)
+    tall = (rng.random((300, 40)) < 0.2) * rng.integers(1, 6, (300, 40))       # more users than items: no transpose
+    svd = TruncatedSVD(n_components=12, random_state=42)
+    ref_u = svd.fit_transform(tall.astype(np.float64))
+    uf2, itf2, s2 = bo.truncated_svd_factors(tall, 12)
+    np.testing.assert_allclose(uf2, ref_u, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(itf2, svd.components_.T, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s2, svd.singular_values_, rtol=1e-12)

@@ -56,7 +56,7 @@ def child(n, b, k, cons):
               f"units={i['last_units']} cands={i['last_candidates']} appends={i['last_appends']} slow_chunks={i['last_slow_chunks']} wasted={i['last_wasted_chunks']} "
               f"compactions={i['last_compactions']} mma_wait_epi={i['mma_wait_epilogue_cycles']/max(1,i['mma_total_cycles']):.3f} "
               f"mma_wait_tma={i['mma_wait_tma_cycles']/max(1,i['mma_total_cycles']):.3f} "
-              f"epi[wait,slow,compact,end,-,hold,ld]={[round(x / max(1, i['epilogue_cycles'][4]), 3) for x in i['epilogue_cycles']]} tile_cycles={i['epilogue_cycles'][4] / max(1, i['sm_count'] * 16) / max(1, (n // 256) * ((b + 255) // 256) / (i['sm_count'] // 2)):.0f}", flush=True)
+              f"epi[wait,slow,compact,end,-,hold,ld]={[round(x / max(1, i['epilogue_cycles'][4]), 3) for x in i['epilogue_cycles']]} rounds_kcyc={[round(x / max(1, i['sm_count'] // 2) / 1e3) for x in i['round_cycles']]} round_wait_kcyc={[round(x / max(1, i['sm_count'] // 2) / 1e3) for x in i['round_wait_cycles']]} tile_cycles={i['epilogue_cycles'][4] / max(1, i['sm_count'] * 16) / max(1, (n // 256) * ((b + 255) // 256) / (i['sm_count'] // 2)):.0f}", flush=True)
 
 
 if __name__ == "__main__":
