@@ -233,13 +233,13 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   if (p.n_tiles < 1) p.n_tiles = 1;
   const int hw_groups = tc ? h->sm_count / h->cta_group : h->sm_count * 2;
   // Catalog splits.  Every unit pays a fixed price (cold candidate streams, a sorted + published prefix at its end),
-  // so units should be long (>= ~131k catalog rows) but there must be enough of them to fill the machine evenly: pick the
-  // smallest split count within reach whose static round-robin schedule keeps >= 97% of the CTA groups busy.
-  const long long mem_cap = (5ll << 29) / (static_cast<long long>(p.b_pad) * kCap * 8 * (tc ? kTcSubStreams : 1));   // 2.5 GiB
+  // so units should be long (>= ~64k catalog rows) but there must be enough of them to fill the machine evenly: pick the
+  // split count near that target whose static round-robin schedule keeps the most CTA groups busy.
+  const long long mem_cap = (5ll << 29) / (static_cast<long long>(p.b_pad) * (tc ? kCapTc : kCap) * 8 * (tc ? kTcSubStreams : 1));   // 2.5 GiB
   long long s_cap = p.n_tiles;
   if (s_cap > 64) s_cap = 64;
   if (s_cap > mem_cap) s_cap = mem_cap > 0 ? mem_cap : 1;
-  long long s_lo = p.n_tiles / (131072 / p.tile_items);     // ~131k catalog rows per unit
+  long long s_lo = p.n_tiles / (65536 / p.tile_items);      // ~64k catalog rows per unit
   const long long s_fill = (hw_groups + p.n_qblocks - 1) / p.n_qblocks;    // enough units to occupy every group once
   if (s_lo < s_fill) s_lo = s_fill;
   if (s_lo < 1) s_lo = 1;
@@ -426,7 +426,8 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   }
   if (dump == nullptr) {
     const size_t slots = static_cast<size_t>(P.n_slot_splits) * P.n_sub * plan.b_pad;
-    BB_CUDA(h, w->cand.ensure(slots * kCap * sizeof(uint64_t)));
+    P.cap = tc ? kCapTc : kCap;
+    BB_CUDA(h, w->cand.ensure(slots * static_cast<size_t>(P.cap) * sizeof(uint64_t)));
     BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
     BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
     BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));

@@ -247,7 +247,7 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
       for (int j = 0; j < 32 && s0 + j < n_slots; ++j) {
         const int cnt = __shfl_sync(kFull, my_cnt, j);
         if (cnt == 0) continue;
-        const uint64_t* buf = P.cand + (static_cast<int64_t>(s0 + j) * P.b_pad + q) * kCap;
+        const uint64_t* buf = P.cand + (static_cast<int64_t>(s0 + j) * P.b_pad + q) * P.cap;
         for (int base = 0; base < cnt; base += 32) {
           uint64_t key = (base + lane < cnt) ? __ldcg(buf + base + lane) : 0ull;
           if (static_cast<uint32_t>(key >> 32) < thr) key = 0ull;

@@ -12,6 +12,7 @@ namespace bb {
 
 constexpr int kCap = 256;          // candidate slots per (catalog split, query)
 constexpr int kEpl = kCap / 32;    // keys per lane in the warp sorter
+constexpr int kCapTc = 512;        // tcgen05 scan: one buffer per (split, query) shared by the four column-slice warps
 constexpr int kMaxSel = 128;       // largest k' kept per buffer after a compaction
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -132,7 +133,8 @@ struct ScanParams {
   const int32_t* cons_index;      // per-row index into cons[] (distinct constraint sets) or nullptr
   const uint32_t* class_valid;    // per distinct constraint set: validity bitmap over local rows (mask kernel) or nullptr
   int64_t class_words;            // words per class bitmap
-  // candidate buffers: slot = (split * n_sub + sub) * b_pad + row; cand[slot * kCap + i], cnt[slot]
+  // candidate buffers: slot = (split * n_sub + sub) * b_pad + row; cand[slot * cap + i], cnt[slot]
+  int32_t cap;            // keys per candidate buffer: kCap (exact fp32 scan) or kCapTc (tcgen05 scan)
   int32_t n_sub;          // buffers per (split, row): the tcgen05 epilogue uses one per column half
   uint64_t* cand;
   int32_t* cand_cnt;
@@ -340,11 +342,14 @@ __device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, i
     const int tail = cnt - kMaxSel;
     if (tail <= 32) kth = warp_compact_merge<1>(buf, cnt, lane);
     else if (tail <= 64) kth = warp_compact_merge<2>(buf, cnt, lane);
-    else kth = warp_compact_merge<4>(buf, cnt, lane);
+    else if (tail <= 128) kth = warp_compact_merge<4>(buf, cnt, lane);
+    else if (tail <= 256) kth = warp_compact_merge<8>(buf, cnt, lane);
+    else kth = warp_compact_n<kCapTc / 32>(buf, cnt, k_sel, lane);
   } else if (cnt <= 32) kth = warp_compact_n<1>(buf, cnt, k_sel, lane);
   else if (cnt <= 64) kth = warp_compact_n<2>(buf, cnt, k_sel, lane);
   else if (cnt <= 128) kth = warp_compact_n<4>(buf, cnt, k_sel, lane);
-  else kth = warp_compact_n<kEpl>(buf, cnt, k_sel, lane);
+  else if (cnt <= kCap) kth = warp_compact_n<kEpl>(buf, cnt, k_sel, lane);
+  else kth = warp_compact_n<kCapTc / 32>(buf, cnt, k_sel, lane);
   *new_thr = (cnt >= k_sel) ? key_score(kth) : -INFINITY;
   __syncwarp();
   return cnt < k_sel ? cnt : k_sel;
@@ -391,7 +396,7 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
     uint32_t v[kPer];
 #pragma unroll
     for (int i = 0; i < kPer; ++i)
-      v[i] = (c[i] >= r) ? static_cast<uint32_t>(__ldcg(P.cand + slot[i] * kCap + (r - 1)) >> 32) : 0u;
+      v[i] = (c[i] >= r) ? static_cast<uint32_t>(__ldcg(P.cand + slot[i] * P.cap + (r - 1)) >> 32) : 0u;
     warp_sort_desc<kPer, uint32_t>(v, lane);
     const int e = need - 1;                         // element e lives in register e>>5 of lane e&31
     uint32_t t = 0u;
@@ -404,16 +409,10 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
   return best;
 }
 
-// After a group of <= 32 appends per lane: compact every row of this warp whose
-// buffer could overflow on the next group, publish its sorted prefix, and raise the
-// row's shared threshold (own k'-th best and the cross-stream refinement).
-// `force_mask`: lanes whose buffer is compacted regardless of fill (unit end: leave a sorted, published prefix).
-// `refine_mask`: lanes whose compaction also runs the cross-stream refinement (warp-uniform value).
-// `headroom`: appends a lane may make before the next call (the buffer must not overflow in between).
-__device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane,
-                                                      unsigned force_mask = 0u, unsigned refine_mask = kFull, int headroom = 32) {
-  __syncwarp();
-  const unsigned need0 = __ballot_sync(kFull, st.cnt > kCap - headroom) | force_mask;
+// Compacts the buffers of the rows in `need0` (a warp-uniform lane mask; lane l holds row l's RowState): sort /
+// merge, publish the sorted prefix, optionally refine across streams, raise the shared threshold.
+__device__ __forceinline__ int warp_compact_rows(const ScanParams& P, RowState& st, int row, int lane, unsigned need0,
+                                                 unsigned refine_mask) {
   if (need0 == 0u) return 0;
   // phase 1: sort / merge every flagged row's buffer (warp-cooperative, one row at a time)
   float my_nt = -INFINITY;
@@ -457,6 +456,19 @@ __device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowSt
     }
   }
   return __popc(need0);
+}
+
+// After a group of <= 32 appends per lane: compact every row of this warp whose
+// buffer could overflow on the next group, publish its sorted prefix, and raise the
+// row's shared threshold (own k'-th best and the cross-stream refinement).
+// `force_mask`: lanes whose buffer is compacted regardless of fill (unit end: leave a sorted, published prefix).
+// `refine_mask`: lanes whose compaction also runs the cross-stream refinement (warp-uniform value).
+// `headroom`: appends a lane may make before the next call (the buffer must not overflow in between).
+__device__ __forceinline__ int warp_compact_if_needed(const ScanParams& P, RowState& st, int row, int lane,
+                                                      unsigned force_mask = 0u, unsigned refine_mask = kFull, int headroom = 32) {
+  __syncwarp();
+  const unsigned need0 = __ballot_sync(kFull, st.cnt > kCap - headroom) | force_mask;
+  return warp_compact_rows(P, st, row, lane, need0, refine_mask);
 }
 
 __device__ __forceinline__ void row_append(const ScanParams& P, RowState& st, float score, int64_t item) {

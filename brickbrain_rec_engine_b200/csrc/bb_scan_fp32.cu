@@ -63,7 +63,7 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
   st.cnt = 0;
   st.sorted = 0;
   st.slot = static_cast<int64_t>(split) * P.n_sub * P.b_pad + (warp < 4 ? own_row : 0);
-  st.buf = P.cand + st.slot * kCap;
+  st.buf = P.cand + st.slot * P.cap;
 
   const int n_slabs = P.k_pad / XK;
   for (int t = t0; t < t1; ++t) {

@@ -46,11 +46,17 @@ __device__ __forceinline__ long long epi_clock() {
 }
 constexpr int kAccStages = 512 / kAccCols;  // TMEM accumulator ring: how far the MMA issuer may run ahead of the epilogue
 constexpr int kTmemCols = 512;              // two accumulators
-constexpr int kEpiWarps = 4 * kTcSubStreams; // kTcSubStreams warps per TMEM lane quarter, each scans a column slice of every tile
+constexpr int kColWarps = 4;                // epilogue warps per TMEM lane quarter (row group), each scans a column slice of every tile
+constexpr int kEpiWarps = 4 * kColWarps;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kChunksPerWarp = (kAccCols / 32) / (kEpiWarps / 4);
-static_assert(kCap - 32 * kChunksPerWarp >= kMaxSel + 32, "candidate buffer too small for this many chunks per epilogue warp");
+// the four column-slice warps of a row group append to ONE buffer per row; it is checked once per tile, and a tile
+// can add at most kTcTile keys to a row
+constexpr int kCompactLine = kCapTc - kTcTile;   // a row whose count crosses this line is compacted at the tile's end
+static_assert(kCompactLine >= kMaxSel, "candidate buffer too small: a compacted row (<= kMaxSel keys) must be below the line");
+static_assert(kTcSubStreams == 1, "one candidate stream per (split, row)");
 constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata of the 32 columns of a chunk
+constexpr int kRowStateBytes = 3 * 128 * 4 + 64;   // per row: count, sorted prefix, threshold; + compaction flags [3 tiles][4 row groups]
 constexpr int kThemeBytes = 32 * 128 * 4;         // per-row allowed-theme bitmaps, word-major [32 words][128 rows]
 constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
 
@@ -63,7 +69,7 @@ template <int CG, bool kRowCons> struct Cfg {
                                            : (kRowCons ? 64 : 96) * 1024 / kBStageBytes;
   static constexpr int kThemeSmem = kRowCons ? kThemeBytes : 0;
   static constexpr int kSmemBytes =
-      kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kColMetaBytes + kThemeSmem + 512 + 1024;
+      kTcMaxKBlocks * kAkbBytes + kStages * kBStageBytes + kColMetaBytes + kThemeSmem + 512 + kRowStateBytes + 1024;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -232,6 +238,38 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ------------------------------------------------------------------ the kernel
+// bar.sync on a named barrier: the four column-slice warps of a row group (128 threads)
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
+// Compaction of the rows in `need` (bit = row of the row group `ew`), split between the group's four warps: warp
+// `half` takes every fourth flagged row.  Row state lives in shared memory; lane l of EVERY warp of the group
+// addresses row l's buffer (`buf`, `slot`, `q`), so a row's pointers are one shuffle away.  Called between two
+// barriers of the row group: nobody appends meanwhile.
+__device__ __forceinline__ int group_compact(const ScanParams& P, unsigned need, unsigned refine_mask, int half, int* s_cnt,
+                                             int* s_sorted, float* s_thr, int ew, uint64_t* buf, int64_t slot, int q, int lane) {
+  unsigned mine = 0u;
+  int i = 0;
+  for (unsigned m = need; m; m &= m - 1, ++i)
+    if ((i & 3) == half) mine |= m & (0u - m);
+  if (mine == 0u) return 0;
+  const int row_in_cta = ew * 32 + lane;
+  RowState st;
+  st.buf = buf;
+  st.slot = slot;
+  st.cnt = s_cnt[row_in_cta];
+  st.sorted = s_sorted[row_in_cta];
+  st.thr = s_thr[row_in_cta];
+  const int n = warp_compact_rows(P, st, q, lane, mine, refine_mask & mine);
+  if ((mine >> lane) & 1u) {
+    s_cnt[row_in_cta] = st.cnt;
+    s_sorted[row_in_cta] = st.sorted;
+    s_thr[row_in_cta] = st.thr;
+  }
+  return n;
+}
+
 template <int CG, bool kRowCons>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
@@ -253,6 +291,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   uint64_t* bar_acc_full = bar_a_full + 2;                     // [kAccStages]  MMA -> epilogue (per CTA)
   uint64_t* bar_acc_empty = bar_acc_full + kAccStages;         // [kAccStages]  epilogue -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + kAccStages);
+  int* s_cnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(bars) + 512);   // [128] keys in the row's buffer
+  int* s_sorted = s_cnt + 128;                                                       // [128] sorted prefix length
+  float* s_thr = reinterpret_cast<float*>(s_sorted + 128);                           // [128] row threshold (after compactions)
+  unsigned* s_flag = reinterpret_cast<unsigned*>(s_thr + 128);                       // [3][4] rows that crossed the compaction line
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -443,19 +485,28 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
       }
       const bool any_theme = __any_sync(kFull, has_theme);
-      RowState st;
-      st.thr = dead ? INFINITY : -INFINITY;
-      st.cnt = 0;
-      st.sorted = 0;
-      const int64_t slot = (static_cast<int64_t>(split) * P.n_sub + half) * P.b_pad + q;
-      st.buf = P.cand + slot * kCap;
-      st.slot = slot;
-      int next_pub = 32;                             // early-publish schedule of a cold stream
+      // ---- one candidate stream per (split, row), shared by the row group's four column-slice warps: count,
+      //      sorted-prefix length and threshold live in shared memory, appends take their slot with a shared-memory
+      //      atomic; the four warps meet at a named barrier once per tile, where rows that crossed the compaction
+      //      line are compacted (split between the four warps) before anyone appends again
+      const int64_t slot = static_cast<int64_t>(split) * P.b_pad + q;
+      uint64_t* const buf = P.cand + slot * kCapTc;
+      const int bar_id = 1 + ew;
+      if (half == 0) {
+        s_cnt[row_in_cta] = 0;
+        s_sorted[row_in_cta] = 0;
+        s_thr[row_in_cta] = dead ? INFINITY : -INFINITY;
+        if (lane < 3) s_flag[lane * 4 + ew] = 0u;
+      }
+      named_bar_sync(bar_id, kColWarps * 32);
+      float thr = dead ? INFINITY : -INFINITY;
       const bool share_thr = !dead && P.dump == nullptr;
       uint32_t thr_next = share_thr ? thr_load(P, q) : kOrdNegInf;   // shared threshold, fetched one tile ahead
+      int tslot = 0;                                 // tile index mod 3: which flag word this tile's appends raise
       for (int t = t0; t < t1; ++t) {
+        thr = fmaxf(thr, s_thr[row_in_cta]);
         if (share_thr) {
-          st.thr = fmaxf(st.thr, ord2f(thr_next));
+          thr = fmaxf(thr, ord2f(thr_next));
           thr_next = thr_load(P, q);
         }
         {
@@ -526,14 +577,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           // item must not drag the warp into the slow path -- two thirds of the triggers were of that kind)
           unsigned pm = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= st.thr) ? (1u << j) : 0u;
-          pm &= ~__ballot_sync(kFull, col_item >= P.n_items);
-          if (!(P.debug_flags & 128)) pm &= class_word;      // (flag 128: A/B switch, trigger on unmasked scores)
+          for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= thr) ? (1u << j) : 0u;
+          pm &= class_word & ~__ballot_sync(kFull, col_item >= P.n_items);
           if (__any_sync(kFull, pm != 0u) && !(P.debug_flags & 1)) {
             // ---- slow path, entered only when some row of this warp has a live candidate
             ++stat_slow;
             const long long c0 = epi_clock();
-            pm &= class_word;
             if (use_cons) {
               // column owners publish their item's unpacked metadata (prefetched above) in shared memory;
               // every row then checks only ITS OWN passing columns (trip count = max passes of one row)
@@ -554,7 +603,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             if (!__any_sync(kFull, pm != 0u)) ++stat_wasted;
             else {
-              // ---- a masked-in candidate exists
               while (__any_sync(kFull, pm != 0u)) {
                 if (pm != 0u) {
                   const int j = __ffs(pm) - 1;
@@ -573,7 +621,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                   const int64_t item = item0 + chunk * 32 + j;
                   // cheap predicates were applied above; only rows with allow bitmaps / exclusion lists pay the call
                   if (item != self_local && (!needs_full || item_ok(P, q, item))) {
-                    row_append(P, st, sc, item);
+                    const int pos = atomicAdd(s_cnt + row_in_cta, 1);
+                    __stcg(buf + pos, make_key(sc, static_cast<uint32_t>(item + P.id_offset)));
+                    if (pos == kCompactLine) atomicOr(s_flag + tslot * 4 + ew, 1u << lane);   // (exactly one append crosses the line)
                     ++stat_appends;
                   }
                 }
@@ -582,33 +632,38 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             cyc_slow += epi_clock() - c0;
           }
         }
-        // deferred compaction (after the accumulator was released): a tile appends at most 32 keys per chunk
         if (P.dump == nullptr && !(P.debug_flags & 3)) {
-          // (only with in-scan refinement switched on, debug flags 16 / 32: cold streams publish a small sorted
-          //  prefix early so that the row's concurrently cold streams can find a shared threshold sooner)
-          const bool pub_now = !dead && st.thr == -INFINITY && st.cnt >= next_pub && (P.debug_flags & (16 | 32)) != 0;
-          if (pub_now) next_pub *= 2;                // 32, 64, 128, then only the regular overflow trigger
-          const unsigned early = __ballot_sync(kFull, pub_now);
-          // (in-scan compactions only publish; measured: refining here costs more stall than the tighter threshold saves --
-          //  the refinement at unit end is what keeps later units warm)
-          const long long c0 = epi_clock();
-          const int nc = warp_compact_if_needed(P, st, q, lane, early, (P.debug_flags & 16) ? kFull : ((P.debug_flags & 32) ? early : 0u), 32 * kChunksPerWarp);
-          stat_compact += nc;
-          if (nc) cyc_compact += epi_clock() - c0;
+          // ---- tile end: every append of this tile by the row group's four warps is complete and visible
+          named_bar_sync(bar_id, kColWarps * 32);
+          const unsigned need = s_flag[tslot * 4 + ew];          // rows that crossed the line in this tile (written before the barrier)
+          const int pslot = tslot == 0 ? 2 : tslot - 1;
+          if (half == 0 && lane == 0) s_flag[pslot * 4 + ew] = 0u;   // recycle the flag word of tile t-1 (next written in tile t+2)
+          if (need != 0u) {
+            const long long c0 = epi_clock();
+            stat_compact += group_compact(P, need, 0u, half, s_cnt, s_sorted, s_thr, ew, buf, slot, q, lane);
+            cyc_compact += epi_clock() - c0;
+            named_bar_sync(bar_id, kColWarps * 32);              // new counts / thresholds are visible before the next append
+          }
         }
+        if (++tslot == 3) tslot = 0;
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
       if (P.dump == nullptr) {
         // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units
         // that scan this row later start from everything this stream has learnt
         // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
-        const unsigned fresh = __ballot_sync(kFull, !dead && st.cnt >= 8);
-        // (one of the row's column-slice streams refines; the others only sort + publish)
         const long long c0 = epi_clock();
-        stat_compact += warp_compact_if_needed(P, st, q, lane, fresh, (half == 0 && !(P.debug_flags & 8)) ? kFull : 0u);
+        if (P.debug_flags & 3) named_bar_sync(bar_id, kColWarps * 32);
+        const unsigned fresh = __ballot_sync(kFull, !dead && s_cnt[row_in_cta] >= 8);
+        stat_compact += group_compact(P, fresh, (P.debug_flags & 8) ? 0u : kFull, half, s_cnt, s_sorted, s_thr, ew, buf, slot, q, lane);
+        named_bar_sync(bar_id, kColWarps * 32);
         cyc_end += epi_clock() - c0;
-        P.cand_cnt[slot] = st.cnt;
-        if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));
+        if (half == 0) {
+          const int c = s_cnt[row_in_cta];
+          P.cand_cnt[slot] = c;
+          if (P.stat_candidates != nullptr && c > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(c));
+        }
+        named_bar_sync(bar_id, kColWarps * 32);                  // the next unit re-initializes the row state
       }
     }
     if (P.stat_candidates != nullptr && P.dump == nullptr) {
