@@ -48,7 +48,9 @@ def parse():
     p.add_argument("--constraint-form", default="indexed", choices=["indexed", "per-query"],
                    help="indexed: distinct constraint sets + per-query index (class bitmaps); per-query: one descriptor per query")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--no-share", action="store_true", help="N>1: do not share running thresholds between the shards")
+    p.add_argument("--share-thresholds", action="store_true",
+                   help="N>1: shards raise each other's per-query running thresholds through NVLink peer memory "
+                        "(bb_import_peer_thresholds); measured SLOWER on 8 B200s (813k vs 869k queries/s), off by default")
     p.add_argument("--cpu-sample-items", type=int, default=1_000_000)
     p.add_argument("--cpu-sample-queries", type=int, default=1024)
     return p.parse_args()
@@ -192,7 +194,7 @@ def run_ours(args):
     eng = ScoringEngine(hi - lo, d, f, device=local, id_offset=lo, k_max=128, max_batch=b)
     # row-sharded catalog: the shards' per-query running thresholds are one logical array over NVLink peer memory
     share = False
-    if world > 1 and not args.no_share:
+    if world > 1 and args.share_thresholds:
         from brickbrain_rec_engine_b200.sharded import exchange_threshold_handles
         share = exchange_threshold_handles(eng)
     descs, theme_bitmaps, themes = scenario_descriptors(b)
@@ -357,7 +359,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -423,11 +425,29 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else (library banners such as NCCL's
+    version line, warnings) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
     args = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)          # keep the real stdout for the JSON line ...
+    os.dup2(2, 1)                 # ... and send every other write to fd 1 (C libraries included) to stderr
     if args.impl == "reference":
         run_reference(args)
     else:

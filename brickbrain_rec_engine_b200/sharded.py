@@ -50,7 +50,7 @@ class ShardedSearch:
     """Couples a per-rank engine (anything with ``search`` and ``merge_topk``) with the
     candidate all-gather.  ``engine.id_offset`` must equal this rank's ``shard_bounds`` begin."""
 
-    def __init__(self, engine, group=None, share_thresholds: bool = True):
+    def __init__(self, engine, group=None, share_thresholds: bool = False):
         if dist is None or not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialized (one process per GPU)")
         self.engine = engine
