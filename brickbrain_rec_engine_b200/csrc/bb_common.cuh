@@ -160,7 +160,8 @@ struct ScanParams {
   unsigned long long* stat_candidates;
   int32_t* err_flag;      // set by watchdogs before trapping
   uint32_t* wave_counter; // producers that finished issuing a unit's loads (keeps the CTA groups of a wave in step)
-  int32_t debug_flags;    // perf triage (env BB_DEBUG_FLAGS): 1 = epilogue never inserts, 2 = epilogue skips TMEM loads
+  int32_t debug_flags;    // perf triage (env BB_DEBUG_FLAGS): 1 = epilogue never inserts, 2 = epilogue skips TMEM loads,
+                          // 4 = no wave barrier, 8 = no cross-stream refinement at unit end
 };
 
 __device__ __forceinline__ void split_tile_range(const ScanParams& P, int split, int& t0, int& t1) {

@@ -13,9 +13,10 @@
 //     double buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
 //   * work unit = (query block, catalog split); units are dealt round-robin to groups.
 //
-// Warp roles (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA),
+// Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA),
 // 2 = TMEM allocator, 3 = idle, 4..19 = epilogue (TMEM lane quarter = warp % 4; the four
-// warps of a quarter split the tile's 256 columns; one thread per (query row, column slice) = one stream).
+// warps of a quarter -- a row group -- split the tile's 256 columns and share ONE candidate
+// stream per (catalog split, query row): row state in shared memory, one named barrier per tile).
 //
 // Roofline: tensor core.  2*128*256*k_pad flop per CTA tile; catalog bytes
 // 256*k_pad*2 per group tile.
