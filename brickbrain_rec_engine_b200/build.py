@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libbrickscore.so")
-SOURCES = ["bb_api.cu", "bb_aux.cu", "bb_scan_fp32.cu", "bb_scan_tc.cu", "bb_itemitem.cu", "bb_spmm.cu"]
+SOURCES = ["bb_api.cu", "bb_aux.cu", "bb_scan_fp32.cu", "bb_scan_tc.cu", "bb_itemitem.cu", "bb_spmm.cu", "bb_scan_small.cu"]
 HEADERS = ["bb_common.cuh", "bb_kernels.h", os.path.join("..", "..", "include", "brickscore.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

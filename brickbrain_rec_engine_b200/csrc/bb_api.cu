@@ -309,6 +309,15 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   if (q->n_constraints != 0 && q->constraints == nullptr) return fail(h, BB_ERR_INVALID, "constraints is NULL");
 
   plan = make_plan(h, B, tc);
+  // exact fp32 search of a small batch (the reference's one-query-per-call pattern): stream the catalog once at HBM
+  // speed (bb_scan_small.cu) instead of running the 128-row FFMA tile scan on padded rows
+  const bool small = !tc && dump == nullptr && B <= kSmallBatch && static_cast<size_t>(kSmallBatch) * h->k_pad * 4 <= 200 * 1024 &&
+                     getenv("BB_NO_SMALL") == nullptr;
+  if (small) {
+    plan.n_splits = small_scan_splits(h->cfg.n_items);
+    plan.pilot_tiles = 0;
+    plan.n_units = plan.n_splits * B;
+  }
   const int D = h->cfg.dim, F = h->cfg.cf_dim, KP = h->k_pad;
 
   // ---- validate constraint indices on the host when the descriptors are host memory
@@ -414,7 +423,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.n_sub = tc ? kTcSubStreams : 1;
   P.pilot_tiles = dump == nullptr ? plan.pilot_tiles : 0;
   P.n_slot_splits = plan.n_splits + (P.pilot_tiles > 0 ? 1 : 0);
-  P.n_units = P.pilot_tiles > 0 ? plan.n_units : plan.n_qblocks * plan.n_splits;
+  P.n_units = (P.pilot_tiles > 0 || small) ? plan.n_units : plan.n_qblocks * plan.n_splits;
   P.tile_items = plan.tile_items;
   P.dump = dump;
   P.stat_candidates = w->stats();
@@ -500,6 +509,13 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
       h->tmap_e_ok = true;
     }
     BB_CUDA(h, launch_scan_tc(P, &w->tmap_q, &h->tmap_e, h->cta_group, plan.n_groups, stream));
+  } else if (small) {
+    int bt = 1;
+    while (bt < B) bt <<= 1;
+    BB_CUDA(h, w->misc.ensure(static_cast<size_t>(bt) * static_cast<size_t>(h->cfg.n_items) * sizeof(float)));
+    BB_CUDA(h, launch_scan_small(P, static_cast<const float*>(w->q_f32.p), h->cat_f32, static_cast<float*>(w->misc.p),
+                                 h->sm_count, stream));
+    h->launches++;
   } else {
     BB_CUDA(h, launch_scan_fp32(P, static_cast<const float*>(w->q_f32.p), h->cat_f32, stream));
   }

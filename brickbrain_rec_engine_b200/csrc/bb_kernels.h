@@ -34,6 +34,12 @@ cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const
 cudaError_t launch_pack_meta(const int32_t* num_parts, const int16_t* year, const int16_t* theme, int64_t n_rows,
                              int2* out, cudaStream_t stream);
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream);
+// exact fp32 path for B <= kSmallBatch queries (bb_scan_small.cu): dense score strip [B_template x n_items] + per-split
+// selection into the candidate slots (slot = split * b_pad + q, P.cap keys each); merge_emit finishes
+constexpr int kSmallBatch = 16;
+int small_scan_splits(int64_t n_items);
+cudaError_t launch_scan_small(const ScanParams& P, const float* q_f32, const float* cat_f32, float* scores, int sm_count,
+                              cudaStream_t stream);
 // Y[n_rows x L] = CSR(n_rows x *) * X[* x L], fp32 values, fp64 X / Y (bb_spmm.cu); L <= 128
 cudaError_t launch_csr_spmm_f64(int64_t n_rows, int64_t nnz, const int64_t* indptr, const int32_t* indices, const float* values,
                                 const double* X, int L, double* Y, int sm_count, cudaStream_t stream);

@@ -543,3 +543,33 @@ def test_svd_training_matches_reference_factors(bb, golden_dir):
     cf.train_svd_model(50)
     assert cf.svd_model is None
     eng.close()
+
+
+def test_small_batch_exact_path_matches_tile_scan(bb):
+    """B <= 16 exact-fp32 searches take the HBM-streaming path (bb_scan_small.cu); it must return what the 128-row
+    FFMA tile scan returns (BB_NO_SMALL=1) and what the oracle returns: filters, self exclusion, constraints,
+    exclusion lists, ragged catalog size, k up to 128."""
+    n, d, f = 70001, 384, 64
+    themes, emb, itf, parts, year, theme = _catalog(n, d, f, 77)
+    eng = bb.ScoringEngine(n, d, f)
+    eng.load_catalog(emb=emb, item_factors=itf, num_parts=parts, year=year, theme_id=theme)
+    rated = {j: np.sort(np.random.default_rng(200 + j).choice(n, 40, replace=False)).astype(np.int32) for j in range(6)}
+    e_unit = bo.l2_normalize_rows(emb)
+    for b, k in ((1, 10), (3, 50), (16, 128)):
+        q_items = (np.arange(b, dtype=np.int32) * 997 + 5) % n
+        u = synth.cf_factors(b, f, 31 + b)
+        descs, specs = _scenario_descs(bb, eng, themes, rated, b)
+        kw = dict(q_item=q_items, q_cf=u, w_content=0.4, w_cf=0.6, constraints=descs, self_id=q_items, precision="fp32")
+        s1, i1 = eng.search(k, **kw)
+        assert eng.info()["last_units"] == b * max(1, -(-n // 32768))          # the small path ran
+        os.environ["BB_NO_SMALL"] = "1"
+        try:
+            s2, i2 = eng.search(k, **kw)
+        finally:
+            del os.environ["BB_NO_SMALL"]
+        ref = bo.fused_hybrid_scores(e_unit[q_items], u, e_unit, itf, np.full(b, 0.4, np.float32), np.full(b, 0.6, np.float32))
+        valid = np.stack([bo.constraint_mask(s, parts, year, theme) for s in specs])
+        rid, rs = bo.fused_hybrid_topk(ref, k, valid=valid, self_ids=q_items, exclusions=[rated[j % 6] for j in range(b)])
+        assert_topk_equal(rid, rs, i1, s1, what=f"small path b={b}")
+        assert_topk_equal(rid, rs, i2, s2, what=f"tile path b={b}")
+    eng.close()
