@@ -6,9 +6,9 @@
 //        query operands in shared memory; scores[q][item] = <query operand q, catalog operand item> (fp32 FMA,
 //        three shuffles per (row, query)).  Bound: HBM, 4*k_pad B per item (1792 B at 384+64); the dense score
 //        strip written back is B*4 B per item.
-//   K_b select_small_kernel: one CTA per (catalog split, query): validity (bounds, self, hard constraints, allow /
-//        exclusion lists through item_ok) is checked only for scores above the running k'-th best; the split's
-//        sorted top-k' goes to the query's candidate slot, and the regular merge_emit kernel finishes.
+//   K_b select_small_kernel: one CTA per (catalog split, query): scores above the running k'-th best are staged and
+//        validated in batches at the merger's flush (bounds, self, hard constraints, allow / exclusion lists through
+//        item_ok); the split's sorted top-k' goes to the query's candidate slot, and the regular merge_emit kernel finishes.
 #include "bb_common.cuh"
 #include "bb_kernels.h"
 
@@ -69,10 +69,18 @@ struct SmallMerger {
     for (int i = lane; i < kCap; i += 32) stage[i] = 0ull;
     __syncwarp();
   }
-  __device__ void flush() {
+  // `validate`: the new keys were staged unchecked; every lane checks its own (bounds, self, hard constraints, allow /
+  // exclusion lists) NOW, four at a time and all lanes busy -- checking at offer time made every loop iteration with a
+  // passing score wait for a chain of dependent global loads (self id, descriptor, metadata, list search)
+  __device__ void flush(const ScanParams& P, int q, bool validate) {
     uint64_t v[kEpl];
 #pragma unroll
     for (int i = 0; i < kEpl; ++i) v[i] = stage[(i << 5) | lane];
+    if (validate) {
+#pragma unroll
+      for (int i = kEpl / 2; i < kEpl; ++i)
+        if (v[i] != 0ull && !item_ok(P, q, static_cast<int64_t>(key_id(v[i])) - P.id_offset)) v[i] = 0ull;
+    }
     __syncwarp();
     warp_sort_desc<kEpl>(v, lane);
 #pragma unroll
@@ -81,13 +89,13 @@ struct SmallMerger {
     n_new = 0;
     __syncwarp();
   }
-  __device__ void offer(uint64_t key) {
+  __device__ void offer(uint64_t key, const ScanParams& P, int q, bool validate) {
     const unsigned m = __ballot_sync(kFull, key != 0ull);
     if (m == 0) return;
     if (key != 0ull) stage[kCap / 2 + n_new + __popc(m & ((1u << lane) - 1u))] = key;
     n_new += __popc(m);
     __syncwarp();
-    if (n_new + 32 > kCap / 2) flush();
+    if (n_new + 32 > kCap / 2) flush(P, q, validate);
   }
 };
 
@@ -115,20 +123,19 @@ __global__ void __launch_bounds__(128) select_small_kernel(const ScanParams P, c
       uint64_t key = 0ull;
       if (item < hi) {
         key = make_key(v[j], static_cast<uint32_t>(item + P.id_offset));
-        // validity only for scores that can still enter the top-k': after the first flushes this is rare
-        if (key <= mg.floor_key || !item_ok(P, q, item)) key = 0ull;
+        if (key <= mg.floor_key) key = 0ull;       // cannot enter the top-k' any more; survivors are validated at the flush
       }
-      mg.offer(key);
+      mg.offer(key, P, q, true);
     }
   }
-  mg.flush();
+  mg.flush(P, q, true);
   __syncthreads();
   if (warp == 0) {
     // fold the other warps' sorted halves in, then publish the split's top-k' for merge_emit
     for (int w2 = 1; w2 < 4; ++w2) {
-      for (int x = 0; x < kCap / 2; x += 32) mg.offer(stages[w2][x + lane]);
+      for (int x = 0; x < kCap / 2; x += 32) mg.offer(stages[w2][x + lane], P, q, false);   // (already validated)
     }
-    mg.flush();
+    mg.flush(P, q, false);
     const int64_t slot = static_cast<int64_t>(split) * P.b_pad + q;
     uint64_t* out = P.cand + slot * P.cap;
     int cnt = 0;
