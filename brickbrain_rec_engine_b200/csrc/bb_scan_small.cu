@@ -15,7 +15,8 @@
 namespace bb {
 namespace {
 
-constexpr int kItemsPerWarp = 4;   // 8 lanes per catalog row
+constexpr int kRowsPerGroup = 2;                       // catalog rows an 8-lane group scores per query-operand read
+constexpr int kItemsPerWarp = 4 * kRowsPerGroup;       // 8 lanes per catalog row, 4 groups per warp
 
 template <int B>
 __global__ void __launch_bounds__(256) score_small_kernel(const float* __restrict__ q_f32, const float* __restrict__ cat_f32,
@@ -29,32 +30,45 @@ __global__ void __launch_bounds__(256) score_small_kernel(const float* __restric
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int64_t n_groups = (n_items + kItemsPerWarp - 1) / kItemsPerWarp;
   for (int64_t g = warp0; g < n_groups; g += n_warps) {
-    const int64_t item = g * kItemsPerWarp + sub;
-    float acc[B];
+    // the group's rows: item0 + r * 4 (so that the four groups of a warp touch 4 consecutive rows per step)
+    const int64_t item0 = g * kItemsPerWarp + sub;
+    float acc[kRowsPerGroup][B];
 #pragma unroll
-    for (int q = 0; q < B; ++q) acc[q] = 0.f;
-    if (item < n_items) {
-      const float4* row = reinterpret_cast<const float4*>(cat_f32 + item * k_pad);
+    for (int r = 0; r < kRowsPerGroup; ++r)
+#pragma unroll
+      for (int q = 0; q < B; ++q) acc[r][q] = 0.f;
 #pragma unroll 2
-      for (int i = l8; i < n4; i += 8) {
-        const float4 e = __ldcs(row + i);          // streamed once: do not keep it in L2 ahead of the query strip
+    for (int i = l8; i < n4; i += 8) {
+      float4 e[kRowsPerGroup];
 #pragma unroll
-        for (int q = 0; q < B; ++q) {
-          const float4 a = s_q[q * n4 + i];
-          acc[q] = fmaf(a.x, e.x, acc[q]);
-          acc[q] = fmaf(a.y, e.y, acc[q]);
-          acc[q] = fmaf(a.z, e.z, acc[q]);
-          acc[q] = fmaf(a.w, e.w, acc[q]);
+      for (int r = 0; r < kRowsPerGroup; ++r) {
+        const int64_t item = item0 + r * 4;
+        // streamed once: do not keep it in L2 ahead of the score strip
+        e[r] = item < n_items ? __ldcs(reinterpret_cast<const float4*>(cat_f32 + item * k_pad) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        const float4 a = s_q[q * n4 + i];                  // one shared-memory read serves kRowsPerGroup rows
+#pragma unroll
+        for (int r = 0; r < kRowsPerGroup; ++r) {
+          acc[r][q] = fmaf(a.x, e[r].x, acc[r][q]);
+          acc[r][q] = fmaf(a.y, e[r].y, acc[r][q]);
+          acc[r][q] = fmaf(a.z, e[r].z, acc[r][q]);
+          acc[r][q] = fmaf(a.w, e[r].w, acc[r][q]);
         }
       }
     }
 #pragma unroll
-    for (int q = 0; q < B; ++q) {
-      float v = acc[q];
-      v += __shfl_xor_sync(kFull, v, 4);
-      v += __shfl_xor_sync(kFull, v, 2);
-      v += __shfl_xor_sync(kFull, v, 1);
-      if (l8 == 0 && item < n_items) scores[static_cast<int64_t>(q) * n_items + item] = v;
+    for (int r = 0; r < kRowsPerGroup; ++r) {
+      const int64_t item = item0 + r * 4;
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        float v = acc[r][q];
+        v += __shfl_xor_sync(kFull, v, 4);
+        v += __shfl_xor_sync(kFull, v, 2);
+        v += __shfl_xor_sync(kFull, v, 1);
+        if (l8 == 0 && item < n_items) scores[static_cast<int64_t>(q) * n_items + item] = v;
+      }
     }
   }
 }
@@ -165,7 +179,7 @@ cudaError_t launch_score_b(const float* q_f32, const float* cat_f32, int64_t n_i
 }  // namespace
 
 int small_scan_splits(int64_t n_items) {
-  int64_t s = (n_items + 32767) / 32768;
+  int64_t s = (n_items + 4095) / 4096;          // the selection is a latency-bound single-CTA loop: keep it short
   if (s < 1) s = 1;
   if (s > 64) s = 64;
   return static_cast<int>(s);
