@@ -18,7 +18,7 @@ cudaError_t launch_scan_fp32(const ScanParams& P, const float* Q, const float* E
 constexpr int kTcTile = 256;      // catalog rows per MMA tile (UMMA N); 512 / kTcTile TMEM accumulator stages (N=128 is smem-bandwidth bound: measured 995 vs 1524 TFLOP/s MMA-only)
 constexpr int kTcRowsPerCta = 128;
 constexpr int kTcMaxKBlocks = 7;  // resident query operand: 7 x 64 bf16 columns
-constexpr int kTcSubStreams = 1;  // epilogue warps per TMEM lane quarter = candidate streams per (split, row)
+constexpr int kTcSubStreams = 1;  // candidate streams per (split, row): the four column-slice warps of a row group share one
 // cta_group: 1 or 2.  tmap_q / tmap_e are CUtensorMap objects (host memory, passed by value to the kernel).
 cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* tmap_e, int cta_group, int n_groups,
                            cudaStream_t stream);

@@ -283,3 +283,30 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_cf_training_host_logic():
+    """cf_training: the LU normalizer (P @ L without a dense permutation) equals scipy's permute_l form, the CSR pair
+    is built as the kernel expects it, and training refuses to run without the CUDA engine (no CPU fallback)."""
+    import torch
+    from scipy import linalg
+    from brickbrain_rec_engine_b200 import cf_training
+    rng = np.random.default_rng(0)
+    for shape in ((300, 7), (64, 64), (2000, 60)):
+        x = rng.standard_normal(shape)
+        ref, _ = linalg.lu(x, permute_l=True)
+        np.testing.assert_allclose(cf_training._lu_pl(torch.from_numpy(x)).numpy(), ref, rtol=0, atol=1e-12)
+    dense = ((rng.random((40, 25)) < 0.2) * rng.integers(1, 6, (40, 25))).astype(np.float32)
+    pair = cf_training.CsrPair(dense, "cpu")
+    assert pair.shape == (40, 25) and pair.nnz == int((dense != 0).sum())
+    ip, ix, v = (t.numpy() for t in pair.a)
+    assert ip.dtype == np.int64 and ix.dtype == np.int32 and v.dtype == np.float32 and ip[-1] == pair.nnz
+    back = np.zeros_like(dense)
+    for r in range(40):
+        back[r, ix[ip[r]:ip[r + 1]]] = v[ip[r]:ip[r + 1]]
+    assert np.array_equal(back, dense)
+    ipt, ixt, vt = (t.numpy() for t in pair.at)
+    assert ipt.shape[0] == 26 and ipt[-1] == pair.nnz and (np.diff(ixt[ipt[3]:ipt[4]]) > 0).all()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            cf_training.truncated_svd(None, dense, 5)
