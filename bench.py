@@ -192,11 +192,13 @@ def run_ours(args):
     # ---------------- resident catalog shard (synthetic, generated on the device)
     lo, hi = shard_bounds(n, world, rank)
     eng = ScoringEngine(hi - lo, d, f, device=local, id_offset=lo, k_max=128, max_batch=b)
-    # row-sharded catalog: the shards' per-query running thresholds are one logical array over NVLink peer memory
-    share = False
-    if world > 1 and args.share_thresholds:
-        from brickbrain_rec_engine_b200.sharded import exchange_threshold_handles
-        share = exchange_threshold_handles(eng)
+    # row-sharded catalog: per-shard search + NCCL all-gather of the candidates + merge (ShardedSearch); optionally the
+    # shards' per-query running thresholds become one logical array over NVLink peer memory
+    ss = None
+    if world > 1:
+        from brickbrain_rec_engine_b200 import ShardedSearch
+        ss = ShardedSearch(eng, share_thresholds=args.share_thresholds)
+    share = ss is not None and ss.shared
     descs, theme_bitmaps, themes = scenario_descriptors(b)
     eng.set_theme_sets(theme_bitmaps)
     # queries carry (index into) the batch's distinct constraint sets; --distinct-constraints per-query disables it
@@ -258,16 +260,12 @@ def run_ours(args):
                                 constraints=cons_np, constraint_index=cidx_np, self_id=qh["self_id"].numpy(),
                                 precision=args.precision, out=(host_out_s.numpy(), host_out_i.numpy()))
             return s, ids
-        eng.search(k, q_emb=qh["q"].numpy(), q_cf=qh["u"].numpy(), w_content=0.4, w_cf=0.6, constraints=cons_np,
-                   constraint_index=cidx_np, self_id=qh["self_id"].numpy(), precision=args.precision, out=(out_s, out_i),
-                   share_thresholds=share)
-        dist.all_gather_into_tensor(gather_s.view(-1), out_s.view(-1))
-        dist.all_gather_into_tensor(gather_i.view(-1), out_i.view(-1))
-        ms, mi = eng.merge_topk(gather_s, gather_i, k)
-        host_out_s.copy_(ms, non_blocking=True)
-        host_out_i.copy_(mi, non_blocking=True)
-        torch.cuda.synchronize()
-        return host_out_s, host_out_i
+        # N > 1: the user-facing call is ShardedSearch.search with HOST arrays -- every rank uploads 1/world of the
+        # replicated batch, the slices are all-gathered over NVLink, then shard search + candidate all-gather + merge;
+        # the merged result is read back into pinned host memory
+        return ss.search(k, host_out=(host_out_s, host_out_i), q_emb=qh["q"].numpy(), q_cf=qh["u"].numpy(), w_content=0.4,
+                         w_cf=0.6, constraints=cons_np, constraint_index=cidx_np, self_id=qh["self_id"].numpy(),
+                         precision=args.precision)
 
     def barrier():
         if world > 1:

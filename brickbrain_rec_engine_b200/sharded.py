@@ -61,17 +61,41 @@ class ShardedSearch:
         if share_thresholds and self.world_size > 1 and hasattr(engine, "export_threshold_handle"):
             self.shared = exchange_threshold_handles(engine, group)
 
-    def search(self, k: int, **kwargs):
-        """Same keyword arguments as ``ScoringEngine.search``; returns the GLOBAL top-k on every rank."""
+    #: per-query arrays of ``ScoringEngine.search`` and the dtype the engine expects
+    _PER_QUERY = {"q_emb": np.float32, "q_cf": np.float32, "q_item": np.int32, "self_id": np.int32, "constraint_index": np.int32}
+
+    def _spread_host_inputs(self, kwargs, b):
+        """Host (NumPy) query batches are replicated on every rank.  Instead of every rank pushing the whole batch
+        through its own PCIe link, each rank uploads 1/world of every per-query array and the slices are
+        all-gathered over NVLink into device tensors (total H2D = one batch, not world batches)."""
+        per = b // self.world_size
+        dev = f"cuda:{self.engine.device}"
+        for name, dt in self._PER_QUERY.items():
+            v = kwargs.get(name)
+            if v is None or torch.is_tensor(v):
+                continue
+            t = torch.from_numpy(np.ascontiguousarray(v, dtype=dt))
+            part = t[self.rank * per:(self.rank + 1) * per].to(dev, non_blocking=True)
+            full = torch.empty((b,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(full.view(-1), part.reshape(-1), group=self.group)
+            kwargs[name] = full
+
+    def search(self, k: int, host_out=None, **kwargs):
+        """Same keyword arguments as ``ScoringEngine.search``; returns the GLOBAL top-k on every rank.
+        ``host_out``: optional (scores, ids) CPU tensors (pinned) that receive the merged result of a host call."""
         if self.shared:
             kwargs["share_thresholds"] = True
-        # host (NumPy) callers over an NCCL group: the per-shard result stays on the device for the gather + merge
-        on_device = (self.world_size > 1 and kwargs.get("out") is None and dist.get_backend(self.group) == "nccl"
-                     and not any(torch.is_tensor(v) and v.is_cuda for v in kwargs.values()))
-        if on_device:
+        nccl = self.world_size > 1 and dist.get_backend(self.group) == "nccl"
+        host_call = not any(torch.is_tensor(v) and v.is_cuda for v in kwargs.values())
+        if nccl and host_call:
             b = next(len(kwargs[n]) for n in ("q_emb", "q_item", "q_cf") if kwargs.get(n) is not None)
-            dev = f"cuda:{self.engine.device}"
-            kwargs["out"] = (torch.empty((b, k), dtype=torch.float32, device=dev), torch.empty((b, k), dtype=torch.int32, device=dev))
+            if b % self.world_size == 0 and b >= self.world_size:
+                self._spread_host_inputs(kwargs, b)
+            # the per-shard result stays on the device for the gather + merge
+            if kwargs.get("out") is None:
+                dev = f"cuda:{self.engine.device}"
+                kwargs["out"] = (torch.empty((b, k), dtype=torch.float32, device=dev),
+                                 torch.empty((b, k), dtype=torch.int32, device=dev))
         scores, ids = self.engine.search(k, **kwargs)
         if self.world_size == 1:
             return scores, ids
@@ -85,5 +109,12 @@ class ShardedSearch:
         dist.all_gather_into_tensor(all_i.view(-1), i_t.reshape(-1).contiguous(), group=self.group)
         if as_torch:
             ms, mi = self.engine.merge_topk(all_s, all_i, k)
-            return (ms.cpu().numpy(), mi.cpu().numpy()) if on_device else (ms, mi)
+            if nccl and host_call:
+                if host_out is not None:
+                    host_out[0].copy_(ms, non_blocking=True)
+                    host_out[1].copy_(mi, non_blocking=True)
+                    torch.cuda.synchronize(self.engine.device)
+                    return host_out[0].numpy(), host_out[1].numpy()
+                return ms.cpu().numpy(), mi.cpu().numpy()
+            return ms, mi
         return self.engine.merge_topk(all_s.numpy(), all_i.numpy(), k)
