@@ -69,7 +69,7 @@ class ShardedSearch:
         through its own PCIe link, each rank uploads 1/world of every per-query array and the slices are
         all-gathered over NVLink into device tensors (total H2D = one batch, not world batches)."""
         per = b // self.world_size
-        dev = f"cuda:{self.engine.device}"
+        dev = f"cuda:{self.engine.device}" if dist.get_backend(self.group) == "nccl" else "cpu"   # (gloo: CPU tests)
         for name, dt in self._PER_QUERY.items():
             v = kwargs.get(name)
             if v is None or torch.is_tensor(v):
@@ -87,12 +87,12 @@ class ShardedSearch:
             kwargs["share_thresholds"] = True
         nccl = self.world_size > 1 and dist.get_backend(self.group) == "nccl"
         host_call = not any(torch.is_tensor(v) and v.is_cuda for v in kwargs.values())
-        if nccl and host_call:
+        if self.world_size > 1 and host_call:
             b = next(len(kwargs[n]) for n in ("q_emb", "q_item", "q_cf") if kwargs.get(n) is not None)
             if b % self.world_size == 0 and b >= self.world_size:
                 self._spread_host_inputs(kwargs, b)
             # the per-shard result stays on the device for the gather + merge
-            if kwargs.get("out") is None:
+            if nccl and kwargs.get("out") is None:
                 dev = f"cuda:{self.engine.device}"
                 kwargs["out"] = (torch.empty((b, k), dtype=torch.float32, device=dev),
                                  torch.empty((b, k), dtype=torch.int32, device=dev))

@@ -257,6 +257,13 @@ ref = bo.fused_hybrid_scores(q, u, bo.l2_normalize_rows(emb), itf, np.full(b, .4
 rid, rs = bo.fused_hybrid_topk(ref, k)
 assert np.array_equal(np.asarray(i), rid), (rank, i, rid)
 np.testing.assert_allclose(np.asarray(s), rs, rtol=1e-6)
+# batch divisible by the world size: every rank uploads 1/world of the host batch and the slices are all-gathered
+b2 = 8
+sid = (np.arange(b2, dtype=np.int32) * 37) % n
+s2, i2 = bb.ShardedSearch(eng).search(k, q_emb=q[:b2], q_cf=u[:b2], w_content=0.4, w_cf=0.6, self_id=sid)
+rid2, rs2 = bo.fused_hybrid_topk(ref[:b2], k, self_ids=sid)
+assert np.array_equal(np.asarray(i2), rid2), (rank, i2, rid2)
+np.testing.assert_allclose(np.asarray(s2), rs2, rtol=1e-6)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
