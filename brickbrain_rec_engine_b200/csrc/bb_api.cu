@@ -265,8 +265,9 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
   p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
-  // pilot: one short unit per query block over the first tiles, before anything else.  Measured neutral on B200
-  // (cold streams already share thresholds through the early publishes), so it is opt-in: BB_PILOT=1.
+  // pilot: one short unit per query block over the first tiles, before anything else.  Measured slightly slower on
+  // B200 (the first ~8k rows of a cold stream cost most of its appends wherever they are scanned, and the pilot adds
+  // a scheduling round with half the machine idle), so it is opt-in: BB_PILOT=1.
   p.pilot_tiles = (tc && h->cfg.n_items >= 163840 && getenv("BB_PILOT") != nullptr) ? 8192 / p.tile_items : 0;
   const long long pilot_slots = p.pilot_tiles > 0 ? (static_cast<long long>(p.n_qblocks) + p.n_groups - 1) / p.n_groups * p.n_groups : 0;
   p.n_units = static_cast<int>(pilot_slots + units);

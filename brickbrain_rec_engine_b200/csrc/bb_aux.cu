@@ -107,11 +107,6 @@ __global__ void pack_meta_kernel(const int32_t* __restrict__ num_parts, const in
   out[i] = make_int2(p, (y & 0xffff) | (t << 16));
 }
 
-__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
-}
-
 __global__ void gather_rows_kernel(const float* __restrict__ cat_f32, const __nv_bfloat16* __restrict__ cat_bf16,
                                    int k_pad, int dim, int64_t id_offset, int64_t n_items,
                                    const int32_t* __restrict__ ids, int n, float* __restrict__ out, int32_t* err_flag) {
@@ -451,12 +446,6 @@ cudaError_t launch_pack_meta(const int32_t* num_parts, const int16_t* year, cons
                              int2* out, cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   pack_meta_kernel<<<blocks_for(n_rows, 256), 256, 0, stream>>>(num_parts, year, theme, n_rows, out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  fill_u32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(p, v, n);
   return cudaGetLastError();
 }
 

@@ -33,7 +33,6 @@ cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const
                                 cudaStream_t stream);
 cudaError_t launch_pack_meta(const int32_t* num_parts, const int16_t* year, const int16_t* theme, int64_t n_rows,
                              int2* out, cudaStream_t stream);
-cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream);
 // exact fp32 path for B <= kSmallBatch queries (bb_scan_small.cu): dense score strip [B_template x n_items] + per-split
 // selection into the candidate slots (slot = split * b_pad + q, P.cap keys each); merge_emit finishes
 constexpr int kSmallBatch = 16;
