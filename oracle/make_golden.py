@@ -183,6 +183,19 @@ def main():
                         ids_filter=np.array(ids_cf_f), scores_filter=np.array(sc_cf_f))
     print("cf_golden: factors", uf.shape, itf.shape)
 
+    # ------------------------------------------------------------------ CF training, more users than items (sklearn's
+    # randomized SVD does NOT transpose then): the reference's train_svd_model on a 300 x 96 pivot
+    n_tall_users, n_tall_items = 300, 96
+    tall = synth.rating_matrix(n_tall_users, n_tall_items, seed=52, lo=8, hi=24)
+    frame_t = rh.make_set_frame(synth.set_nums(n_tall_items), [f"Set {i}" for i in range(n_tall_items)],
+                                np.full(n_tall_items, 2020), np.ones(n_tall_items), np.full(n_tall_items, 100), ["x"] * n_tall_items)
+    cf_t = rh.build_cf(rs, None, frame_t, list(range(1, n_tall_users + 1)), tall, None, None)
+    cf_t.svd_model = None
+    cf_t.train_svd_model()
+    np.savez_compressed(os.path.join(OUT, "svd_tall_golden.npz"), ratings=tall.astype(np.int8),
+                        user_factors=np.asarray(cf_t.user_factors), item_factors=np.asarray(cf_t.item_factors))
+    print("svd_tall_golden: factors", np.asarray(cf_t.user_factors).shape, np.asarray(cf_t.item_factors).shape)
+
     # ------------------------------------------------------------------ hybrid: _combine_recommendations + end-to-end with constraints
     con2 = rh.SqliteShimConnection(sn, [f"Set {i}" for i in range(n)], yr_, th_, np_, themes,
                                    synth.user_lists(8, n, 30, seed=61), synth.user_lists(8, n, 20, seed=62))

@@ -526,6 +526,10 @@ def test_svd_training_matches_reference_factors(bb, golden_dir):
     uf, itf, s = cf_training.truncated_svd(eng, ratings, g["user_factors"].shape[1])
     np.testing.assert_allclose(uf, g["user_factors"], rtol=0, atol=1e-8)
     np.testing.assert_allclose(itf, g["item_factors"], rtol=0, atol=1e-9)
+    gt = _golden(golden_dir, "svd_tall_golden.npz")          # 300 users x 96 items: no transpose inside the SVD
+    uft, itft, _ = cf_training.truncated_svd(eng, gt["ratings"].astype(np.float32), gt["user_factors"].shape[1])
+    np.testing.assert_allclose(uft @ itft.T, gt["user_factors"] @ gt["item_factors"].T, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(itft, gt["item_factors"], rtol=0, atol=1e-7)
     rng = np.random.default_rng(5)
     tall = ((rng.random((4000, 600)) < 0.03) * rng.integers(1, 6, (4000, 600))).astype(np.float32)
     ouf, oitf, os_ = bo.truncated_svd_factors(tall, 50)

@@ -158,6 +158,11 @@ def test_svd_training_oracle_reproduces_reference_factors(golden_dir):
     uf, itf, s = bo.truncated_svd_factors(ratings, g["user_factors"].shape[1])
     np.testing.assert_allclose(uf, g["user_factors"], rtol=0, atol=1e-10)
     np.testing.assert_allclose(itf, g["item_factors"], rtol=0, atol=1e-12)
+    # more users than items (no transpose inside the randomized SVD): factors trained by the reference itself
+    gt = np.load(os.path.join(golden_dir, "svd_tall_golden.npz"), allow_pickle=False)
+    uft, itft, _ = bo.truncated_svd_factors(gt["ratings"].astype(np.float64), gt["user_factors"].shape[1])
+    np.testing.assert_allclose(uft, gt["user_factors"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(itft, gt["item_factors"], rtol=0, atol=1e-12)
     from sklearn.decomposition import TruncatedSVD
     rng = np.random.default_rng(3)
     tall = (rng.random((300, 40)) < 0.2) * rng.integers(1, 6, (300, 40))       # more users than items: no transpose
