@@ -29,6 +29,7 @@ BB_PREC_BF16 = 1
 BB_PREC_BF16_RESCORE = 2
 BB_Q_SCORES_AS_L2 = 1
 BB_Q_SHARE_THRESHOLDS = 2
+BB_Q_EMB_PRENORMALIZED = 4
 BB_C_ALWAYS_FALSE = 1
 BB_IPC_HANDLE_BYTES = 64
 
@@ -76,7 +77,8 @@ class bb_query_batch(C.Structure):
                 ("q_item", C.c_void_p), ("q_cf", C.c_void_p), ("w_content", C.c_void_p), ("w_cf", C.c_void_p),
                 ("w_content_all", C.c_float), ("w_cf_all", C.c_float), ("constraints", C.c_void_p),
                 ("n_constraints", C.c_int32), ("constraint_index", C.c_void_p), ("self_id", C.c_void_p), ("precision", C.c_int32),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32), ("allow_bitmaps", C.c_void_p), ("n_allow", C.c_int32),
+                ("n_excl_per_query", C.c_int32), ("excl_lists", C.c_void_p)]
 
 
 class bb_info(C.Structure):
@@ -111,8 +113,12 @@ PROTOTYPES = {
     "bb_item_item_topk": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "bb_debug_scores": (C.c_int, [_P, C.POINTER(bb_query_batch), _P, _P]),
     "bb_csr_spmm_f64": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, C.c_int32, _P, _P]),
-    "bb_export_threshold_handle": (C.c_int, [_P, _P]),
-    "bb_import_peer_thresholds": (C.c_int, [_P, C.c_int32, _P]),
+    "bb_comm_export": (C.c_int, [_P, _P]),
+    "bb_comm_import": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "bb_comm_link_local": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "bb_search_sharded": (C.c_int, [_P, C.POINTER(bb_query_batch), C.c_int32, _P, _P, _P]),
+    "bb_sharded_scatter": (C.c_int, [_P, C.POINTER(bb_query_batch), C.c_int32, _P]),
+    "bb_sharded_collect": (C.c_int, [_P, _P, _P, _P]),
 }
 
 _lib = None

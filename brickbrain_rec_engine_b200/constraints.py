@@ -16,7 +16,7 @@ from __future__ import annotations
 import logging
 import re
 import time
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from datetime import datetime
 from enum import Enum
 from typing import Any, Dict, List, Optional, Sequence
@@ -80,6 +80,8 @@ class ConstraintResult:
     applied_constraints: List[HardConstraint]
     performance_stats: Dict[str, Any]
     constraint_sql: str = ""
+    # (not in the reference) the validity bitmap on the GPU, reused by the searches of the same request
+    device_bitmap: Any = field(default=None, repr=False, compare=False)
 
 
 # kwarg -> (type, description template); order = emission order of create_constraint_set (:140-259)
@@ -112,6 +114,15 @@ class CompiledConstraint:
     exclude_wishlisted_user: Optional[Any] = None
 
 
+def theme_bits_for(themes: Dict[int, str], theme_ids=None) -> int:
+    """Bitmap width (multiple of 32, >= 1024) that holds every theme id of the ``themes`` table and of the catalog's
+    ``theme_id`` column -- pass it as ``ScoringEngine(theme_bits=...)``."""
+    top = max([int(t) for t in themes] + [0])
+    if theme_ids is not None and len(theme_ids):
+        top = max(top, int(np.max(theme_ids)))
+    return max(1024, (top + 32) // 32 * 32)
+
+
 class ConstraintCompiler:
     """Host-side folding of a ``HardConstraint`` list into ``bb_constraint`` fields.
 
@@ -136,8 +147,12 @@ class ConstraintCompiler:
     def _bitmap(self, ids) -> np.ndarray:
         bm = np.zeros(self.theme_words, dtype=np.uint32)
         for t in ids:
-            if 0 <= t < self.theme_bits:
-                bm[t >> 5] |= np.uint32(1 << (t & 31))
+            if not 0 <= t < self.theme_bits:
+                # the reference's `theme_id = ANY(ids)` would match such a theme; a bitmap that cannot hold it would
+                # silently change the result -- size theme_bits from the themes table instead (theme_bits_for)
+                raise ValueError(f"theme id {t} does not fit the engine's theme bitmaps ({self.theme_bits} bits): "
+                                 "create the engine with theme_bits >= max theme id + 1")
+            bm[t >> 5] |= np.uint32(1 << (t & 31))
         return bm
 
     def compile(self, constraints: Sequence[HardConstraint]) -> CompiledConstraint:
@@ -228,6 +243,10 @@ class HardConstraintFilter:
         self.set_nums = list(set_nums)
         self.index_of = {s: i for i, s in enumerate(self.set_nums)}
         self.compiler = ConstraintCompiler(themes, theme_bits=engine.theme_words * 32)
+        too_big = [t for t in themes if not 0 <= int(t) < engine.theme_words * 32]
+        if too_big:
+            raise ValueError(f"theme ids {sorted(too_big)[:5]}... do not fit the engine's theme bitmaps "
+                             f"({engine.theme_words * 32} bits): create the engine with theme_bits=theme_bits_for(themes)")
         self._theme_cache = self.compiler._theme_cache
         self._constraint_cache: Dict = {}
         self._set_metadata_cache: Dict = {}
@@ -240,6 +259,7 @@ class HardConstraintFilter:
             for user, ids in (table or {}).items():
                 self._excl_index[(kind, user)] = len(lists)
                 lists.append(np.asarray(ids, dtype=np.int32))
+        self._excl_lists = lists
         if lists:
             engine.set_exclusion_lists(lists)
         self._theme_bitmaps: List[np.ndarray] = []
@@ -281,6 +301,21 @@ class HardConstraintFilter:
                                       description="Must be currently available for purchase"))
         return out
 
+    def replace_rated_lists(self, rated: Dict[Any, Sequence[int]]) -> Dict[Any, int]:
+        """Re-uploads the exclusion lists with new already-rated lists (after a factor re-training): owned / wishlisted
+        lists keep their indices, rated lists follow.  Returns {user: list index}."""
+        keep = [(key, idx) for key, idx in self._excl_index.items() if key[0] != "rated"]
+        keep.sort(key=lambda kv: kv[1])
+        lists = [self._excl_lists[idx] for _, idx in keep]
+        self._excl_index = {key: i for i, (key, _) in enumerate(keep)}
+        out = {}
+        for user, ids in rated.items():
+            self._excl_index[("rated", user)] = out[user] = len(lists)
+            lists.append(np.asarray(ids, dtype=np.int32))
+        self._excl_lists = lists
+        self.engine.set_exclusion_lists(lists)
+        return out
+
     def _theme_set_index(self, bitmap: np.ndarray) -> int:
         key = bitmap.tobytes()
         if key not in self._theme_bitmap_index:
@@ -311,7 +346,11 @@ class HardConstraintFilter:
         logger.info("Applying %d hard constraints...", len(constraints))
         try:
             descs = [self.descriptor(constraints)] + [self.descriptor([c]) for c in constraints]
-            bitmaps, counts = self.engine.apply_constraints(np.stack(descs))
+            dev_bitmaps, counts = self.engine.apply_constraints(np.stack(descs), device_out=True)
+            if hasattr(dev_bitmaps, "cpu"):
+                bitmaps = dev_bitmaps.cpu().numpy().view(np.uint32)
+            else:                                  # (CPU test doubles return host arrays)
+                bitmaps, dev_bitmaps = dev_bitmaps, None
             n = len(self.set_nums)
             cand = None
             if candidate_set_nums:
@@ -342,12 +381,16 @@ class HardConstraintFilter:
                         suggested_alternatives=_alternatives(c)))
             ms = (time.perf_counter() - t0) * 1000.0
             self._update_performance_stats(len(constraints), len(valid_set_nums), ms)
-            return ConstraintResult(
+            res = ConstraintResult(
                 valid_set_nums=valid_set_nums, violations=violations, applied_constraints=constraints,
                 performance_stats={"filter_time_ms": ms,
                                    "input_sets": len(candidate_set_nums) if candidate_set_nums else "all",
                                    "output_sets": len(valid_set_nums), "constraint_count": len(constraints)},
                 constraint_sql="")
+            # the validity bitmap stays on the device for the searches that follow (HybridRecommender); with a
+            # candidate pre-filter the host-side AND above is the truth, so nothing is attached
+            res.device_bitmap = dev_bitmaps[0:1] if (dev_bitmaps is not None and cand is None) else None
+            return res
         except Exception as e:  # same contract as the reference: log and re-raise (:314-316)
             logger.error("Error applying hard constraints: %s", e)
             raise

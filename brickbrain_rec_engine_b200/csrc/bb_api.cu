@@ -54,7 +54,16 @@ struct DevBuf {
 
 struct Workspace {
   std::mutex mu;
-  DevBuf q_f32, q_bf16, cand, cand_cnt, pub_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid;
+  DevBuf q_f32, q_bf16, cand, cand_cnt, pub_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid, pilot;
+  // pinned mirrors: host inputs of a call are packed here and cross PCIe in ONE copy; host outputs come back in one
+  unsigned char* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  unsigned char* h_out = nullptr;
+  size_t h_out_cap = 0;
+  cudaEvent_t flag_event = nullptr;   // deferred check of the device error flag after a device-output search
+  bool flag_pending = false;
+  cudaEvent_t stage_event = nullptr;  // the packed host->device copy out of h_stage
+  bool stage_busy = false;
   alignas(64) CUtensorMap tmap_q;
   const void* tmap_q_ptr = nullptr;
   int tmap_q_rows = 0;
@@ -102,10 +111,21 @@ struct bb_handle {
   std::atomic<long long> launches{0};
   std::atomic<long long> last_units{0};
   Workspace* last_ws = nullptr;   // most recently created / used workspace (statistics in bb_get_info)
-  unsigned long long* thr_shared = nullptr;   // per-handle threshold words (exportable to peer ranks), max_batch rows
-  int thr_shared_rows = 0;
-  unsigned long long* peer_thr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int n_peers = 0;
+  // exported communication block (row-sharded catalogs): [4 x rows_cap] threshold + level words | [2] arrival counters
+  // (256 B) | inbox [2][8][slice_cap][k_cap] keys
+  unsigned char* comm = nullptr;
+  size_t comm_bytes = 0;
+  int comm_rows = 0;                 // rows_cap (max_batch padded)
+  int comm_slice_cap = 0, comm_k_cap = 0;
+  size_t comm_arrivals_off = 0, comm_inbox_off = 0;
+  unsigned char* peer_comm[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // by rank (own = comm)
+  bool peer_ipc[8] = {false, false, false, false, false, false, false, false};
+  int comm_rank = 0, comm_world = 1;
+  unsigned long long comm_expected[2] = {0ull, 0ull};   // cumulative arrivals this rank waits for, per parity
+  bool pending_scatter = false;      // bb_sharded_scatter issued, bb_sharded_collect outstanding
+  int pending_slice = 0, pending_parity = 0, pending_mine = 0, pending_k = 0;
+  bool pending_l2 = false;
+  unsigned long long* thr_shared() const { return reinterpret_cast<unsigned long long*>(comm); }
   std::atomic<uint32_t> epoch{0};          // private searches
   std::atomic<uint32_t> shared_epoch{0};   // collective searches (BB_Q_SHARE_THRESHOLDS): same sequence on all ranks
   bool profiling = false;
@@ -154,26 +174,76 @@ bool is_device_ptr(const void* p) {
 
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-// Returns a device view of `p` (`bytes` long): p itself when it is device memory,
-// else a staged copy inside `arena` (the arena must have been sized beforehand).
+// Returns a device view of `p` (`bytes` long): p itself when it is device memory, else a staged copy inside the
+// workspace's staging buffer.  Small host inputs are first packed into the workspace's PINNED mirror and cross PCIe in
+// one cudaMemcpyAsync at flush() (a request with eight small arrays used to pay eight pageable copies); large ones
+// (catalog loads) are copied directly.  Usage: account() every pointer, prepare(), get() in the same order, flush().
 struct Stager {
   bb_handle* h;
-  DevBuf* buf;
-  size_t off = 0;
+  Workspace* w;
   cudaStream_t stream;
-  size_t need = 0;
-  // pass 1: account
+  size_t off = 0, need = 0;
+  bool dev[16] = {};
+  int n_acc = 0, n_get = 0;
+  bool pinned = false, pending = false;
+  static constexpr size_t kPinnedLimit = 8u << 20;
   void account(const void* p, size_t bytes) {
-    if (p != nullptr && !is_device_ptr(p)) need += align256(bytes);
+    const bool d = p != nullptr && is_device_ptr(p);
+    if (n_acc < 16) dev[n_acc] = d;
+    ++n_acc;
+    if (p != nullptr && !d) need += align256(bytes);
   }
-  // pass 2: copy
+  cudaError_t prepare() {
+    cudaError_t e = w->stage.ensure(need + 256);
+    if (e != cudaSuccess) return e;
+    if (need == 0 || need > kPinnedLimit) return cudaSuccess;
+    if (w->stage_event != nullptr && w->stage_busy) {        // the previous call's packed copy must have left the mirror
+      e = cudaEventSynchronize(w->stage_event);
+      w->stage_busy = false;
+      if (e != cudaSuccess) return e;
+    }
+    if (w->h_stage_cap < need) {
+      if (w->h_stage != nullptr) cudaFreeHost(w->h_stage);
+      w->h_stage = nullptr;
+      w->h_stage_cap = 0;
+      const size_t want = need + need / 2 + 4096;
+      if (cudaMallocHost(reinterpret_cast<void**>(&w->h_stage), want) != cudaSuccess) {
+        cudaGetLastError();
+        w->h_stage = nullptr;
+        return cudaSuccess;                                  // fall back to direct copies
+      }
+      w->h_stage_cap = want;
+    }
+    pinned = true;
+    return cudaSuccess;
+  }
   cudaError_t get(const void* p, size_t bytes, const void** out) {
+    const int i = n_get++;
     if (p == nullptr) { *out = nullptr; return cudaSuccess; }
-    if (is_device_ptr(p)) { *out = p; return cudaSuccess; }
-    void* d = static_cast<unsigned char*>(buf->p) + off;
+    const bool d = i < 16 ? dev[i] : is_device_ptr(p);
+    if (d) { *out = p; return cudaSuccess; }
+    void* dst = static_cast<unsigned char*>(w->stage.p) + off;
+    *out = dst;
+    if (pinned) {
+      std::memcpy(w->h_stage + off, p, bytes);
+      pending = true;
+      off += align256(bytes);
+      return cudaSuccess;
+    }
     off += align256(bytes);
-    *out = d;
-    return cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, stream);
+    return cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, stream);
+  }
+  cudaError_t flush() {
+    if (!pending) return cudaSuccess;
+    pending = false;
+    cudaError_t e = cudaMemcpyAsync(w->stage.p, w->h_stage, off, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    if (w->stage_event == nullptr) {
+      e = cudaEventCreateWithFlags(&w->stage_event, cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    w->stage_busy = true;
+    return cudaEventRecord(w->stage_event, stream);
   }
 };
 
@@ -218,7 +288,8 @@ int make_tmap(bb_handle* h, CUtensorMap* out, const void* base, uint64_t rows, i
 }
 
 struct Plan {
-  int n_qblocks, n_tiles, n_splits, n_groups, b_pad, tile_items, pilot_tiles, n_units;
+  int n_qblocks, n_tiles, n_splits, n_groups, b_pad, tile_items, n_units;
+  int pilot_tiles, pilot_splits, pilot_groups;   // threshold-seeding pilot pass over the leading tiles (0 = none)
 };
 
 Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
@@ -265,12 +336,25 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   p.n_splits = static_cast<int>(splits);
   const long long units = static_cast<long long>(p.n_qblocks) * p.n_splits;
   p.n_groups = static_cast<int>(units < hw_groups ? units : hw_groups);
-  // pilot: one short unit per query block over the first tiles, before anything else.  Measured slightly slower on
-  // B200 (the first ~8k rows of a cold stream cost most of its appends wherever they are scanned, and the pilot adds
-  // a scheduling round with half the machine idle), so it is opt-in: BB_PILOT=1.
-  p.pilot_tiles = (tc && h->cfg.n_items >= 163840 && getenv("BB_PILOT") != nullptr) ? 8192 / p.tile_items : 0;
-  const long long pilot_slots = p.pilot_tiles > 0 ? (static_cast<long long>(p.n_qblocks) + p.n_groups - 1) / p.n_groups * p.n_groups : 0;
-  p.n_units = static_cast<int>(pilot_slots + units);
+  p.n_units = static_cast<int>(units);
+  // Pilot pass (threshold seeding): a short first launch over the leading tiles that only records, per query row, the
+  // best valid score of every 8 columns; the (k' + E)-th largest of them seeds the row's threshold, so no stream of the
+  // main scan starts cold (a cold stream appends ~every score of its first tiles and sorts its buffer three or four
+  // times: on a 25k-row catalog that was 90% of the scan).  The pilot tiles are scanned twice; keep them <= 1/4 of the
+  // catalog and <= 8192 rows (1024 group maxima per row).
+  p.pilot_tiles = p.pilot_splits = p.pilot_groups = 0;
+  if (tc && p.n_tiles >= 32 && getenv("BB_NO_PILOT") == nullptr) {
+    int pt = p.n_tiles / 4;
+    if (pt > 8192 / p.tile_items) pt = 8192 / p.tile_items;
+    int ps = hw_groups / p.n_qblocks;
+    if (ps < 1) ps = 1;
+    if (ps > pt) ps = pt;
+    pt = pt / ps * ps;
+    p.pilot_tiles = pt;
+    p.pilot_splits = ps;
+    const long long pu = static_cast<long long>(ps) * p.n_qblocks;
+    p.pilot_groups = static_cast<int>(pu < hw_groups ? pu : hw_groups);
+  }
   return p;
 }
 
@@ -280,10 +364,35 @@ int device_guard(bb_handle* h) {
   return BB_OK;
 }
 
-// Shared front half of bb_search / bb_debug_scores: stage inputs, build the query
-// operands, plan the units, run the scan.  On return `P` describes the candidate state.
+// A search with device outputs returns without synchronizing: its error flag (q_item outside the shard, watchdog)
+// is copied to pinned memory behind the kernels and examined at the NEXT call on the same stream's workspace.
+int check_deferred_flag(bb_handle* h, Workspace* w) {
+  if (!w->flag_pending || w->host_flag == nullptr) return BB_OK;
+  if (cudaEventQuery(w->flag_event) != cudaSuccess) {
+    cudaGetLastError();
+    return BB_OK;                      // still running: examined later
+  }
+  w->flag_pending = false;
+  const int32_t flag = w->host_flag[1];
+  if (flag == 1) return fail(h, BB_ERR_INVALID, "previous search on this stream: q_item / id outside this shard's id range (results invalid)");
+  if (flag != 0) return fail(h, BB_ERR_CUDA, "previous search on this stream: device watchdog code %d", flag);
+  return BB_OK;
+}
+
+int defer_flag_check(bb_handle* h, Workspace* w, cudaStream_t stream) {
+  if (w->host_flag == nullptr) return BB_OK;
+  if (w->flag_event == nullptr) BB_CUDA(h, cudaEventCreateWithFlags(&w->flag_event, cudaEventDisableTiming));
+  BB_CUDA(h, cudaMemcpyAsync(w->host_flag + 1, w->err_flag(), sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  BB_CUDA(h, cudaEventRecord(w->flag_event, stream));
+  w->flag_pending = true;
+  return BB_OK;
+}
+
+// Shared front half of bb_search / bb_search_sharded / bb_debug_scores: stage inputs, build the query operands, plan the
+// units, (pilot pass + threshold seeds,) run the scan.  On return `P` describes the candidate state.
+// `collective`: search of a row-sharded catalog whose ranks share thresholds through the communication block.
 int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, float* dump, cudaStream_t stream,
-             ScanParams& P, Plan& plan) {
+             ScanParams& P, Plan& plan, bool collective) {
   const int B = q->n_queries;
   const int prec = q->precision;
   const bool tc = prec != BB_PREC_FP32;
@@ -308,6 +417,15 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
         return fail(h, BB_ERR_INVALID, "constraint_index[%d] = %d out of range", i, q->constraint_index[i]);
   }
   if (q->n_constraints != 0 && q->constraints == nullptr) return fail(h, BB_ERR_INVALID, "constraints is NULL");
+  if (q->n_allow < 0 || (q->n_allow > 0 && q->allow_bitmaps == nullptr)) return fail(h, BB_ERR_INVALID, "bad per-call allow bitmaps");
+  if (q->n_excl_per_query < 0 || q->n_excl_per_query > 3 || (q->n_excl_per_query > 0 && q->excl_lists == nullptr))
+    return fail(h, BB_ERR_INVALID, "n_excl_per_query must be in [0, 3] (with excl_lists)");
+  const int n_allow = q->allow_bitmaps != nullptr ? q->n_allow : h->n_allow;
+  const int n_qexcl = q->n_excl_per_query;
+  if (n_qexcl > 0 && !is_device_ptr(q->excl_lists)) {
+    for (int64_t i = 0; i < static_cast<int64_t>(B) * n_qexcl; ++i)
+      if (q->excl_lists[i] >= h->n_excl) return fail(h, BB_ERR_INVALID, "excl_lists[%lld] = %d out of range", static_cast<long long>(i), q->excl_lists[i]);
+  }
 
   plan = make_plan(h, B, tc);
   // exact fp32 search of a small batch (the reference's one-query-per-call pattern): stream the catalog once at HBM
@@ -316,17 +434,16 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
                      getenv("BB_NO_SMALL") == nullptr;
   if (small) {
     plan.n_splits = small_scan_splits(h->cfg.n_items);
-    plan.pilot_tiles = 0;
     plan.n_units = plan.n_splits * B;
   }
   const int D = h->cfg.dim, F = h->cfg.cf_dim, KP = h->k_pad;
 
-  // ---- validate constraint indices on the host when the descriptors are host memory
+  // ---- validate descriptor table indices on the host when the descriptors are host memory
   if (q->n_constraints > 0 && !is_device_ptr(q->constraints)) {
     for (int i = 0; i < q->n_constraints; ++i) {
       const bb_constraint& c = q->constraints[i];
       if (c.theme_set >= h->n_theme_sets) return fail(h, BB_ERR_INVALID, "constraint %d: theme_set %d out of range", i, c.theme_set);
-      if (c.allow_bitmap >= h->n_allow) return fail(h, BB_ERR_INVALID, "constraint %d: allow_bitmap %d out of range", i, c.allow_bitmap);
+      if (c.allow_bitmap >= n_allow) return fail(h, BB_ERR_INVALID, "constraint %d: allow_bitmap %d out of range", i, c.allow_bitmap);
       for (int e = 0; e < 3; ++e)
         if (c.excl_list[e] >= h->n_excl) return fail(h, BB_ERR_INVALID, "constraint %d: excl_list %d out of range", i, c.excl_list[e]);
     }
@@ -359,8 +476,10 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     }
   }
 
-  // ---- stage host inputs
-  Stager st{h, &w->stage, 0, stream, 0};
+  // ---- stage host inputs (packed into one pinned buffer, one copy)
+  const int64_t a_words = (h->cfg.n_items + 31) / 32;
+  const size_t allow_bytes = q->allow_bitmaps != nullptr ? sizeof(uint32_t) * static_cast<size_t>(q->n_allow) * a_words : 0;
+  Stager st{h, w, stream};
   st.account(q->q_emb, sizeof(float) * B * D);
   st.account(q->q_item, sizeof(int32_t) * B);
   st.account(q->q_cf, sizeof(float) * B * F);
@@ -369,8 +488,10 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   st.account(q_cons, sizeof(bb_constraint) * n_cons);
   st.account(q->self_id, sizeof(int32_t) * B);
   st.account(q_cidx, sizeof(int32_t) * B);
-  BB_CUDA(h, w->stage.ensure(st.need + 256));
-  const void *d_emb, *d_item, *d_cf, *d_wc, *d_wf, *d_cons, *d_self, *d_cidx;
+  st.account(q->allow_bitmaps, allow_bytes);
+  st.account(q->excl_lists, sizeof(int32_t) * B * n_qexcl);
+  BB_CUDA(h, st.prepare());
+  const void *d_emb, *d_item, *d_cf, *d_wc, *d_wf, *d_cons, *d_self, *d_cidx, *d_allow, *d_qexcl;
   BB_CUDA(h, st.get(q->q_emb, sizeof(float) * B * D, &d_emb));
   BB_CUDA(h, st.get(q->q_item, sizeof(int32_t) * B, &d_item));
   BB_CUDA(h, st.get(q->q_cf, sizeof(float) * B * F, &d_cf));
@@ -379,24 +500,23 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   BB_CUDA(h, st.get(q_cons, sizeof(bb_constraint) * n_cons, &d_cons));
   BB_CUDA(h, st.get(q->self_id, sizeof(int32_t) * B, &d_self));
   BB_CUDA(h, st.get(q_cidx, sizeof(int32_t) * B, &d_cidx));
+  BB_CUDA(h, st.get(q->allow_bitmaps, allow_bytes, &d_allow));
+  BB_CUDA(h, st.get(q->excl_lists, sizeof(int32_t) * B * n_qexcl, &d_qexcl));
+  BB_CUDA(h, st.flush());
 
-  // ---- query operands
+  // ---- control block (statistics, wave counters, error flag) and query operands (padding rows are written as zeros
+  //      by the kernel)
+  BB_CUDA(h, cudaMemsetAsync(w->ctl, 0, 512, stream));
   const size_t qf_bytes = sizeof(float) * static_cast<size_t>(plan.b_pad) * KP;
   const size_t qb_bytes = sizeof(__nv_bfloat16) * static_cast<size_t>(plan.b_pad) * KP;
   BB_CUDA(h, w->q_f32.ensure(qf_bytes));
   BB_CUDA(h, w->q_bf16.ensure(qb_bytes));
-  if (plan.b_pad > B) {
-    BB_CUDA(h, cudaMemsetAsync(static_cast<float*>(w->q_f32.p) + static_cast<size_t>(B) * KP, 0,
-                               sizeof(float) * static_cast<size_t>(plan.b_pad - B) * KP, stream));
-    BB_CUDA(h, cudaMemsetAsync(static_cast<__nv_bfloat16*>(w->q_bf16.p) + static_cast<size_t>(B) * KP, 0,
-                               sizeof(__nv_bfloat16) * static_cast<size_t>(plan.b_pad - B) * KP, stream));
-  }
-  BB_CUDA(h, cudaMemsetAsync(w->err_flag(), 0, sizeof(int32_t), stream));
   BB_CUDA(h, launch_prep_queries(static_cast<const float*>(d_emb), static_cast<const int32_t*>(d_item),
                                  static_cast<const float*>(d_cf), static_cast<const float*>(d_wc),
-                                 static_cast<const float*>(d_wf), q->w_content_all, q->w_cf_all, B, D, F, KP,
-                                 h->cfg.metric, h->cat_f32, h->cat_bf16, h->cfg.id_offset, h->cfg.n_items,
-                                 static_cast<float*>(w->q_f32.p), w->q_bf16.p, w->err_flag(), stream));
+                                 static_cast<const float*>(d_wf), q->w_content_all, q->w_cf_all, B, plan.b_pad, D, F, KP,
+                                 (q->flags & BB_Q_EMB_PRENORMALIZED) ? BB_METRIC_IP : h->cfg.metric, h->cat_f32, h->cat_bf16,
+                                 h->cfg.id_offset, h->cfg.n_items, static_cast<float*>(w->q_f32.p), w->q_bf16.p,
+                                 w->err_flag(), stream));
   h->launches++;
 
   // ---- candidate state
@@ -412,19 +532,20 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   P.cons_stride = (q_cidx == nullptr && n_cons == B && B > 1) ? 1 : 0;
   P.cons_index = static_cast<const int32_t*>(d_cidx);
   P.self_id = static_cast<const int32_t*>(d_self);
+  P.q_excl = static_cast<const int32_t*>(d_qexcl);
+  P.q_excl_n = n_qexcl;
   P.theme_sets = h->theme_sets;
   P.theme_words = h->theme_words;
-  P.allow_bitmaps = h->allow;
-  P.allow_words = h->allow_words;
+  P.allow_bitmaps = q->allow_bitmaps != nullptr ? static_cast<const uint32_t*>(d_allow) : h->allow;
+  P.allow_words = q->allow_bitmaps != nullptr ? a_words : h->allow_words;
   P.excl_off = h->excl_off;
   P.excl_ids = h->excl_ids;
   P.n_qblocks = plan.n_qblocks;
   P.n_splits = plan.n_splits;
   P.n_tiles = plan.n_tiles;
   P.n_sub = tc ? kTcSubStreams : 1;
-  P.pilot_tiles = dump == nullptr ? plan.pilot_tiles : 0;
-  P.n_slot_splits = plan.n_splits + (P.pilot_tiles > 0 ? 1 : 0);
-  P.n_units = (P.pilot_tiles > 0 || small) ? plan.n_units : plan.n_qblocks * plan.n_splits;
+  P.n_slot_splits = plan.n_splits;
+  P.n_units = small ? plan.n_units : plan.n_qblocks * plan.n_splits;
   P.tile_items = plan.tile_items;
   P.dump = dump;
   P.stat_candidates = w->stats();
@@ -439,32 +560,32 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     P.cap = tc ? kCapTc : kCap;
     BB_CUDA(h, w->cand.ensure(slots * static_cast<size_t>(P.cap) * sizeof(uint64_t)));
     BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
-    BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
-    BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
+    if (!small) {
+      BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
+      BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
+    }
     P.pub_cnt = static_cast<int32_t*>(w->pub_cnt.p);
-    // collective search of a row-sharded catalog: the threshold words live in the exported per-handle array and
+    P.cand = static_cast<uint64_t*>(w->cand.p);
+    P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
+    // collective search of a row-sharded catalog: the threshold words live in the exported communication block and
     // carry the collective sequence number; every other search uses the workspace's private array
-    const bool shared = (q->flags & BB_Q_SHARE_THRESHOLDS) != 0 && h->n_peers > 0 && plan.b_pad <= h->thr_shared_rows;
-    if (!shared) {
+    if (collective) {
+      P.epoch = ++h->shared_epoch;
+      P.thr_g = h->thr_shared();
+      P.lvl_stride = h->comm_rows;
+      P.n_peers = 0;
+      for (int r = 0; r < h->comm_world; ++r)
+        if (r != h->comm_rank) P.peer_thr[P.n_peers++] = reinterpret_cast<const unsigned long long*>(h->peer_comm[r]);
+    } else {
       const size_t before = w->thr_g.cap;
       BB_CUDA(h, w->thr_g.ensure(static_cast<size_t>(plan.b_pad) * sizeof(unsigned long long)));
       if (w->thr_g.cap != before) BB_CUDA(h, cudaMemsetAsync(w->thr_g.p, 0, w->thr_g.cap, stream));   // epoch 0 = never current
-    }
-    P.cand = static_cast<uint64_t*>(w->cand.p);
-    P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
-    if (shared) {
-      P.epoch = ++h->shared_epoch;
-      P.thr_g = h->thr_shared;
-      P.n_peers = h->n_peers;
-      for (int i = 0; i < h->n_peers; ++i) P.peer_thr[i] = h->peer_thr[i];
-    } else {
       P.epoch = ++h->epoch;
       P.thr_g = static_cast<unsigned long long*>(w->thr_g.p);
       P.n_peers = 0;
+      P.lvl_stride = 0;
     }
     P.wave_counter = w->wave_counter();
-    BB_CUDA(h, cudaMemsetAsync(w->ctl, 0, 192, stream));
-    BB_CUDA(h, cudaMemsetAsync(w->ctl + 256, 0, 256, stream));
   }
 
   // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
@@ -479,9 +600,45 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
         (reinterpret_cast<uintptr_t>(static_cast<unsigned char*>(w->shared_valid.p) + bm_bytes) + 7) & ~static_cast<uintptr_t>(7));
     BB_CUDA(h, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * n_classes, stream));
     BB_CUDA(h, launch_mask(P, n_classes, static_cast<uint32_t*>(w->shared_valid.p), cnt, stream));
-    h->launches++;
+    h->launches += (n_classes + 31) / 32;
     P.class_valid = static_cast<const uint32_t*>(w->shared_valid.p);
     P.class_words = words;
+  }
+
+  // ---- tensor maps
+  if (tc) {
+    if (w->tmap_q_ptr != w->q_bf16.p || w->tmap_q_rows != plan.b_pad) {
+      int rc = make_tmap(h, &w->tmap_q, w->q_bf16.p, static_cast<uint64_t>(plan.b_pad), KP, kTcRowsPerCta);
+      if (rc != BB_OK) return rc;
+      w->tmap_q_ptr = w->q_bf16.p;
+      w->tmap_q_rows = plan.b_pad;
+    }
+    if (!h->tmap_e_ok) {
+      int rc = make_tmap(h, &h->tmap_e, h->cat_bf16, static_cast<uint64_t>(h->cfg.n_items), KP, kTcTile / h->cta_group);
+      if (rc != BB_OK) return rc;
+      h->tmap_e_ok = true;
+    }
+  }
+
+  // ---- pilot pass + threshold seeds (tcgen05 scan; rows whose validity is a bitmap word: no constraints or class mode)
+  const bool pilot = tc && dump == nullptr && plan.pilot_tiles > 0 && (P.cons == nullptr || P.class_valid != nullptr);
+  if (pilot) {
+    const int groups = plan.pilot_tiles * (kTcTile / 8);
+    BB_CUDA(h, w->pilot.ensure(static_cast<size_t>(plan.b_pad) * groups * sizeof(float)));
+    ScanParams PP = P;
+    PP.pilot_mode = 1;
+    PP.pilot_max = static_cast<float*>(w->pilot.p);
+    PP.pilot_groups = groups;
+    PP.n_tiles = plan.pilot_tiles;
+    PP.n_splits = plan.pilot_splits;
+    PP.n_units = plan.n_qblocks * plan.pilot_splits;
+    PP.stat_candidates = nullptr;
+    PP.wave_counter = w->wave_counter() + 1;
+    PP.n_peers = 0;
+    BB_CUDA(h, launch_scan_tc(PP, &w->tmap_q, &h->tmap_e, h->cta_group, plan.pilot_groups, stream));
+    const int64_t pilot_items = static_cast<int64_t>(plan.pilot_tiles) * kTcTile;
+    BB_CUDA(h, launch_seed_thresholds(PP, pilot_items < h->cfg.n_items ? pilot_items : h->cfg.n_items, stream));
+    h->launches += 2;
   }
 
   // ---- scan
@@ -498,17 +655,6 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   }
   if (ev.first != nullptr) BB_CUDA(h, cudaEventRecord(ev.first, stream));
   if (tc) {
-    if (w->tmap_q_ptr != w->q_bf16.p || w->tmap_q_rows != plan.b_pad) {
-      int rc = make_tmap(h, &w->tmap_q, w->q_bf16.p, static_cast<uint64_t>(plan.b_pad), KP, kTcRowsPerCta);
-      if (rc != BB_OK) return rc;
-      w->tmap_q_ptr = w->q_bf16.p;
-      w->tmap_q_rows = plan.b_pad;
-    }
-    if (!h->tmap_e_ok) {
-      int rc = make_tmap(h, &h->tmap_e, h->cat_bf16, static_cast<uint64_t>(h->cfg.n_items), KP, kTcTile / h->cta_group);
-      if (rc != BB_OK) return rc;
-      h->tmap_e_ok = true;
-    }
     BB_CUDA(h, launch_scan_tc(P, &w->tmap_q, &h->tmap_e, h->cta_group, plan.n_groups, stream));
   } else if (small) {
     int bt = 1;
@@ -610,47 +756,104 @@ int bb_create(bb_handle** out, const bb_config* cfg) {
     if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "metadata alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
   }
   if (cfg->max_batch > 0) {
-    h->thr_shared_rows = (cfg->max_batch + 255) / 256 * 256;
-    e = cudaMalloc(reinterpret_cast<void**>(&h->thr_shared), static_cast<size_t>(h->thr_shared_rows) * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(h->thr_shared, 0, static_cast<size_t>(h->thr_shared_rows) * sizeof(unsigned long long));
-    if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "threshold array alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+    // exported communication block of a row-sharded catalog (see CommParams / ScanParams::lvl_stride)
+    h->comm_rows = (cfg->max_batch + 255) / 256 * 256;
+    h->comm_slice_cap = (h->comm_rows + 1) / 2;
+    h->comm_k_cap = cfg->k_max > 0 ? cfg->k_max : kMaxSel;
+    const size_t thr_bytes = align256(static_cast<size_t>(4) * h->comm_rows * sizeof(unsigned long long));
+    h->comm_arrivals_off = thr_bytes;
+    h->comm_inbox_off = thr_bytes + 256;
+    h->comm_bytes = h->comm_inbox_off + static_cast<size_t>(2) * 8 * h->comm_slice_cap * h->comm_k_cap * sizeof(unsigned long long);
+    e = cudaMalloc(reinterpret_cast<void**>(&h->comm), h->comm_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->comm, 0, h->comm_inbox_off);
+    if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "communication block alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+    h->peer_comm[0] = h->comm;
   }
   *out = h;
   return BB_OK;
 }
 
-int bb_export_threshold_handle(bb_handle* h, void* out_handle) {
+namespace {
+void comm_close_peers(bb_handle* h) {
+  for (int r = 0; r < 8; ++r) {
+    if (h->peer_ipc[r] && h->peer_comm[r] != nullptr) cudaIpcCloseMemHandle(h->peer_comm[r]);
+    h->peer_ipc[r] = false;
+    h->peer_comm[r] = nullptr;
+  }
+  cudaGetLastError();
+}
+int comm_reset(bb_handle* h, int rank, int world) {
+  // a (re-)import restarts the collective sequence on every rank
+  h->comm_rank = rank;
+  h->comm_world = world;
+  h->shared_epoch = 0;
+  h->comm_expected[0] = h->comm_expected[1] = 0ull;
+  h->peer_comm[rank] = h->comm;
+  BB_CUDA(h, cudaMemset(h->comm, 0, h->comm_inbox_off));
+  return BB_OK;
+}
+}  // namespace
+
+int bb_comm_export(bb_handle* h, void* out_handle) {
   if (h == nullptr || out_handle == nullptr) return BB_ERR_INVALID;
   int rc = device_guard(h);
   if (rc != BB_OK) return rc;
-  if (h->thr_shared == nullptr) return fail(h, BB_ERR_STATE, "threshold sharing needs bb_config.max_batch > 0");
+  if (h->comm == nullptr) return fail(h, BB_ERR_STATE, "sharded search needs bb_config.max_batch > 0");
   static_assert(sizeof(cudaIpcMemHandle_t) == BB_IPC_HANDLE_BYTES, "ipc handle size");
   cudaIpcMemHandle_t hd;
-  BB_CUDA(h, cudaIpcGetMemHandle(&hd, h->thr_shared));
+  BB_CUDA(h, cudaIpcGetMemHandle(&hd, h->comm));
   std::memcpy(out_handle, &hd, sizeof(hd));
   return BB_OK;
 }
 
-int bb_import_peer_thresholds(bb_handle* h, int32_t n_peers, const void* handles) {
+int bb_comm_import(bb_handle* h, int32_t rank, int32_t world, const void* handles) {
   if (h == nullptr) return BB_ERR_INVALID;
   int rc = device_guard(h);
   if (rc != BB_OK) return rc;
-  if (n_peers < 0 || n_peers > 7 || (n_peers > 0 && handles == nullptr)) return fail(h, BB_ERR_INVALID, "n_peers must be in [0, 7]");
-  if (h->thr_shared == nullptr) return fail(h, BB_ERR_STATE, "threshold sharing needs bb_config.max_batch > 0");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || (world > 1 && handles == nullptr))
+    return fail(h, BB_ERR_INVALID, "bb_comm_import: world must be in [1, 8] and rank in [0, world)");
+  if (h->comm == nullptr) return fail(h, BB_ERR_STATE, "sharded search needs bb_config.max_batch > 0");
   BB_CUDA(h, cudaDeviceSynchronize());
-  for (int i = 0; i < h->n_peers; ++i) cudaIpcCloseMemHandle(h->peer_thr[i]);
-  h->n_peers = 0;
-  for (int i = 0; i < n_peers; ++i) {
+  comm_close_peers(h);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
     cudaIpcMemHandle_t hd;
-    std::memcpy(&hd, static_cast<const unsigned char*>(handles) + static_cast<size_t>(i) * sizeof(hd), sizeof(hd));
+    std::memcpy(&hd, static_cast<const unsigned char*>(handles) + static_cast<size_t>(r) * sizeof(hd), sizeof(hd));
     void* p = nullptr;
     BB_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
-    h->peer_thr[h->n_peers++] = static_cast<unsigned long long*>(p);
+    h->peer_comm[r] = static_cast<unsigned char*>(p);
+    h->peer_ipc[r] = true;
   }
-  // a (re-)import restarts the collective sequence on every rank
-  h->shared_epoch = 0;
-  BB_CUDA(h, cudaMemset(h->thr_shared, 0, static_cast<size_t>(h->thr_shared_rows) * sizeof(unsigned long long)));
-  return BB_OK;
+  return comm_reset(h, rank, world);
+}
+
+int bb_comm_link_local(bb_handle* h, int32_t rank, int32_t world, bb_handle* const* handles) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || handles == nullptr)
+    return fail(h, BB_ERR_INVALID, "bb_comm_link_local: world must be in [1, 8] and rank in [0, world)");
+  if (h->comm == nullptr) return fail(h, BB_ERR_STATE, "sharded search needs bb_config.max_batch > 0");
+  BB_CUDA(h, cudaDeviceSynchronize());
+  comm_close_peers(h);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    const bb_handle* o = handles[r];
+    if (o == nullptr || o->comm == nullptr) return fail(h, BB_ERR_INVALID, "peer %d has no communication block", r);
+    if (o->comm_rows != h->comm_rows || o->comm_k_cap != h->comm_k_cap)
+      return fail(h, BB_ERR_INVALID, "peer %d was created with another max_batch / k_max", r);
+    if (o->cfg.device != h->cfg.device) {
+      int can = 0;
+      BB_CUDA(h, cudaDeviceCanAccessPeer(&can, h->cfg.device, o->cfg.device));
+      if (!can) return fail(h, BB_ERR_UNSUPPORTED, "device %d cannot access device %d", h->cfg.device, o->cfg.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->cfg.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(h, BB_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    h->peer_comm[r] = o->comm;
+  }
+  return comm_reset(h, rank, world);
 }
 
 void bb_destroy(bb_handle* h) {
@@ -662,12 +865,17 @@ void bb_destroy(bb_handle* h) {
     for (DevBuf* b : {&w->q_f32, &w->q_bf16, &w->cand, &w->cand_cnt, &w->pub_cnt, &w->thr_g, &w->out_scores, &w->out_ids, &w->misc,
                       &w->stage, &w->dump, &w->shared_valid})
       b->release();
+    w->pilot.release();
     if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
+    if (w->h_stage != nullptr) cudaFreeHost(w->h_stage);
+    if (w->h_out != nullptr) cudaFreeHost(w->h_out);
+    if (w->flag_event != nullptr) cudaEventDestroy(w->flag_event);
+    if (w->stage_event != nullptr) cudaEventDestroy(w->stage_event);
     if (w->ctl != nullptr) cudaFree(w->ctl);
     delete w;
   }
-  for (int i = 0; i < h->n_peers; ++i) cudaIpcCloseMemHandle(h->peer_thr[i]);
-  if (h->thr_shared) cudaFree(h->thr_shared);
+  comm_close_peers(h);
+  if (h->comm) cudaFree(h->comm);
   if (h->cat_f32) cudaFree(h->cat_f32);
   if (h->cat_bf16) cudaFree(h->cat_bf16);
   if (h->meta) cudaFree(h->meta);
@@ -757,7 +965,10 @@ int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float
   int rc = device_guard(h);
   if (rc != BB_OK) return rc;
   if (row_begin < 0 || n_rows < 0 || row_begin + n_rows > h->cfg.n_items) return fail(h, BB_ERR_INVALID, "row range outside catalog");
-  if (h->cfg.dim > 0 && emb == nullptr) return fail(h, BB_ERR_INVALID, "emb is NULL but dim=%d", h->cfg.dim);
+  // factor-only reload (re-trained CF factors, recommendation_system.py:402-407): emb == NULL keeps the stored
+  // embedding columns and metadata of rows that were loaded before
+  const bool factors_only = h->cfg.dim > 0 && emb == nullptr && item_factors != nullptr && h->loaded;
+  if (h->cfg.dim > 0 && emb == nullptr && !factors_only) return fail(h, BB_ERR_INVALID, "emb is NULL but dim=%d (only a factor reload of a loaded catalog may omit it)", h->cfg.dim);
   if (h->cfg.cf_dim > 0 && item_factors == nullptr) return fail(h, BB_ERR_INVALID, "item_factors is NULL but cf_dim=%d", h->cfg.cf_dim);
   const int D = h->cfg.dim, F = h->cfg.cf_dim, KP = h->k_pad;
   Workspace* w = get_ws(h, stream);
@@ -766,7 +977,7 @@ int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float
   const int64_t chunk = 1 << 18;   // staging granularity for host inputs
   for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
     const int64_t n = (n_rows - r0 < chunk) ? (n_rows - r0) : chunk;
-    Stager st{h, &w->stage, 0, stream, 0};
+    Stager st{h, w, stream};
     const float* e_p = emb ? emb + r0 * D : nullptr;
     const float* f_p = item_factors ? item_factors + r0 * F : nullptr;
     const int32_t* p_p = num_parts ? num_parts + r0 : nullptr;
@@ -779,7 +990,7 @@ int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float
     st.account(t_p, sizeof(int16_t) * n);
     if (st.need > 0) {
       if (w->stage.cap < st.need + 256) BB_CUDA(h, cudaStreamSynchronize(stream));   // previous chunk still reading it
-      BB_CUDA(h, w->stage.ensure(st.need + 256));
+      BB_CUDA(h, st.prepare());
     }
     const void *de, *df, *dp, *dy, *dt;
     BB_CUDA(h, st.get(e_p, sizeof(float) * n * D, &de));
@@ -787,12 +998,14 @@ int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float
     BB_CUDA(h, st.get(p_p, sizeof(int32_t) * n, &dp));
     BB_CUDA(h, st.get(y_p, sizeof(int16_t) * n, &dy));
     BB_CUDA(h, st.get(t_p, sizeof(int16_t) * n, &dt));
+    BB_CUDA(h, st.flush());
     const int64_t row = row_begin + r0;
     BB_CUDA(h, launch_prep_catalog(static_cast<const float*>(de), static_cast<const float*>(df), n, D, F, KP,
                                    h->cfg.metric, h->cat_f32 ? h->cat_f32 + row * KP : nullptr,
                                    h->cat_bf16 ? h->cat_bf16 + row * KP : nullptr, stream));
-    BB_CUDA(h, launch_pack_meta(static_cast<const int32_t*>(dp), static_cast<const int16_t*>(dy),
-                                static_cast<const int16_t*>(dt), n, h->meta + row, stream));
+    if (!factors_only || num_parts != nullptr || year != nullptr || theme_id != nullptr)
+      BB_CUDA(h, launch_pack_meta(static_cast<const int32_t*>(dp), static_cast<const int16_t*>(dy),
+                                  static_cast<const int16_t*>(dt), n, h->meta + row, stream));
     h->launches += 2;
     if (st.need > 0) BB_CUDA(h, cudaStreamSynchronize(stream));   // staging buffer is reused by the next chunk
   }
@@ -810,11 +1023,12 @@ int bb_fetch_embeddings(bb_handle* h, int32_t n, const int32_t* ids, float* out,
   Workspace* w = get_ws(h, stream);
   if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
-  Stager st{h, &w->stage, 0, stream, 0};
+  Stager st{h, w, stream};
   st.account(ids, sizeof(int32_t) * n);
-  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  BB_CUDA(h, st.prepare());
   const void* d_ids;
   BB_CUDA(h, st.get(ids, sizeof(int32_t) * n, &d_ids));
+  BB_CUDA(h, st.flush());
   const bool out_dev = is_device_ptr(out);
   float* d_out = out;
   if (!out_dev) {
@@ -889,11 +1103,8 @@ int bb_set_allow_bitmaps(bb_handle* h, int32_t n_bitmaps, const uint32_t* bitmap
   return BB_OK;
 }
 
-int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {
-  if (h == nullptr) return BB_ERR_INVALID;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = device_guard(h);
-  if (rc != BB_OK) return rc;
+namespace {
+int search_checks(bb_handle* h, const bb_query_batch* q, int32_t k, const void* out_scores, const void* out_ids) {
   if (q == nullptr || out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
   if (q->struct_size != sizeof(bb_query_batch)) return fail(h, BB_ERR_INVALID, "bb_query_batch.struct_size mismatch");
   if (!h->loaded) return fail(h, BB_ERR_STATE, "catalog not loaded");
@@ -901,41 +1112,178 @@ int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_score
   if (h->cfg.max_batch > 0 && q->n_queries > h->cfg.max_batch) return fail(h, BB_ERR_INVALID, "n_queries %d > max_batch %d", q->n_queries, h->cfg.max_batch);
   if (k <= 0 || k > kMaxSel || (h->cfg.k_max > 0 && k > h->cfg.k_max)) return fail(h, BB_ERR_INVALID, "k=%d outside [1, %d]", k, h->cfg.k_max > 0 ? h->cfg.k_max : kMaxSel);
   if (q->precision < BB_PREC_FP32 || q->precision > BB_PREC_BF16_RESCORE) return fail(h, BB_ERR_INVALID, "unknown precision");
-
-  Workspace* w = get_ws(h, stream);
-  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
-  std::lock_guard<std::mutex> g(w->mu);
-  const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
-  // k' kept per candidate buffer: a multiple of 32; the re-scored path over-fetches.
+  return BB_OK;
+}
+// k' kept per candidate buffer: a multiple of 32; the re-scored path over-fetches.
+int k_select(int k, bool rescore) {
   int k_sel = (k + 31) / 32 * 32;
   if (rescore) {
     k_sel = (k + k / 4 + 8 + 31) / 32 * 32;
     if (k_sel > kMaxSel) k_sel = kMaxSel;
   }
+  return k_sel;
+}
+// Results to the caller: device outputs are written in place (nothing to do); host outputs come back in ONE packed
+// copy ([scores | ids] through the workspace's pinned mirror) followed by the error-flag check.
+struct OutPack {
+  float* d_scores;
+  int32_t* d_ids;
+  bool host;
+};
+int out_prepare(bb_handle* h, Workspace* w, size_t n, float* out_scores, int32_t* out_ids, OutPack& o) {
+  const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
+  if (s_dev != i_dev) return fail(h, BB_ERR_INVALID, "out_scores and out_ids must both be host or both be device memory");
+  o.host = !s_dev;
+  o.d_scores = out_scores;
+  o.d_ids = out_ids;
+  if (o.host) {
+    BB_CUDA(h, w->out_scores.ensure(8 * n + 256));
+    o.d_scores = static_cast<float*>(w->out_scores.p);
+    o.d_ids = reinterpret_cast<int32_t*>(o.d_scores + n);
+    if (w->h_out_cap < 8 * n) {
+      if (w->h_out != nullptr) cudaFreeHost(w->h_out);
+      w->h_out = nullptr;
+      w->h_out_cap = 0;
+      BB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&w->h_out), 8 * n + 4096));
+      w->h_out_cap = 8 * n + 4096;
+    }
+  }
+  return BB_OK;
+}
+int out_finish(bb_handle* h, Workspace* w, size_t n, float* out_scores, int32_t* out_ids, const OutPack& o, cudaStream_t stream) {
+  if (!o.host) return defer_flag_check(h, w, stream);
+  BB_CUDA(h, cudaMemcpyAsync(w->h_out, o.d_scores, 8 * n, cudaMemcpyDeviceToHost, stream));
+  int rc = check_device_flag(h, w, stream);           // synchronizes the stream
+  if (rc != BB_OK) return rc;
+  std::memcpy(out_scores, w->h_out, 4 * n);
+  std::memcpy(out_ids, w->h_out + 4 * n, 4 * n);
+  return BB_OK;
+}
+}  // namespace
+
+int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  rc = search_checks(h, q, k, out_scores, out_ids);
+  if (rc != BB_OK) return rc;
+  Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
+  std::lock_guard<std::mutex> g(w->mu);
+  rc = check_deferred_flag(h, w);
+  if (rc != BB_OK) return rc;
+  const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
+  const int k_sel = k_select(k, rescore);
+  const int b_pad = (q->n_queries + 255) / 256 * 256;
+  // BB_Q_SHARE_THRESHOLDS: the ranks of a row-sharded catalog prune with each other's bounds; results stay local
+  const bool collective = (q->flags & BB_Q_SHARE_THRESHOLDS) != 0 && h->comm_world > 1 && b_pad <= h->comm_rows;
   ScanParams P;
   Plan plan;
-  rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan);
+  rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan, collective);
   if (rc != BB_OK) return rc;
-
-  const int B = q->n_queries;
-  const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
-  float* d_scores = out_scores;
-  int32_t* d_ids = out_ids;
-  if (!s_dev) {
-    BB_CUDA(h, w->out_scores.ensure(sizeof(float) * static_cast<size_t>(B) * k));
-    d_scores = static_cast<float*>(w->out_scores.p);
-  }
-  if (!i_dev) {
-    BB_CUDA(h, w->out_ids.ensure(sizeof(int32_t) * static_cast<size_t>(B) * k));
-    d_ids = static_cast<int32_t*>(w->out_ids.p);
-  }
+  const size_t n = static_cast<size_t>(q->n_queries) * k;
+  OutPack o;
+  rc = out_prepare(h, w, n, out_scores, out_ids, o);
+  if (rc != BB_OK) return rc;
   BB_CUDA(h, launch_merge_emit(P, k, rescore, static_cast<const float*>(w->q_f32.p), h->cat_f32,
-                               (q->flags & BB_Q_SCORES_AS_L2) != 0, d_scores, d_ids, stream));
+                               (q->flags & BB_Q_SCORES_AS_L2) != 0, o.d_scores, o.d_ids, nullptr, stream));
   h->launches++;
-  if (!s_dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d_scores, sizeof(float) * static_cast<size_t>(B) * k, cudaMemcpyDeviceToHost, stream));
-  if (!i_dev) BB_CUDA(h, cudaMemcpyAsync(out_ids, d_ids, sizeof(int32_t) * static_cast<size_t>(B) * k, cudaMemcpyDeviceToHost, stream));
-  if (!s_dev || !i_dev) return check_device_flag(h, w, stream);
+  return out_finish(h, w, n, out_scores, out_ids, o, stream);
+}
+
+namespace {
+void comm_params(const bb_handle* h, int slice, int parity, CommParams& C) {
+  C = CommParams{};
+  for (int r = 0; r < h->comm_world; ++r) {
+    C.inbox[r] = reinterpret_cast<unsigned long long*>(h->peer_comm[r] + h->comm_inbox_off);
+    C.arrivals[r] = reinterpret_cast<unsigned long long*>(h->peer_comm[r] + h->comm_arrivals_off);
+  }
+  C.rank = h->comm_rank;
+  C.world = h->comm_world;
+  C.slice = slice;
+  C.slice_cap = h->comm_slice_cap;
+  C.k_cap = h->comm_k_cap;
+  C.parity = parity;
+}
+}  // namespace
+
+// First half of a collective search: scan this shard against the union thresholds, merge, and deliver this rank's k
+// best keys of every query to the query's owner rank.  Enqueues only (never synchronizes).
+int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  rc = search_checks(h, q, k, q, q);
+  if (rc != BB_OK) return rc;
+  if (h->comm == nullptr || h->comm_world <= 1) return fail(h, BB_ERR_STATE, "sharded search needs bb_config.max_batch > 0 and bb_comm_import / bb_comm_link_local with world > 1");
+  if (h->pending_scatter) return fail(h, BB_ERR_STATE, "bb_sharded_scatter: the previous scatter was not collected");
+  const int B = q->n_queries, world = h->comm_world;
+  const int b_pad = (B + 255) / 256 * 256;
+  const int slice = (B + world - 1) / world;
+  if (b_pad > h->comm_rows || slice > h->comm_slice_cap || k > h->comm_k_cap)
+    return fail(h, BB_ERR_INVALID, "batch %d / k %d exceed the communication block (max_batch %d, k_max %d)", B, k, h->cfg.max_batch, h->comm_k_cap);
+  Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
+  std::lock_guard<std::mutex> g(w->mu);
+  rc = check_deferred_flag(h, w);
+  if (rc != BB_OK) return rc;
+  const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
+  ScanParams P;
+  Plan plan;
+  rc = run_scan(h, w, q, k_select(k, rescore), nullptr, stream, P, plan, true);
+  if (rc != BB_OK) return rc;
+  CommParams C;
+  comm_params(h, slice, static_cast<int>(P.epoch & 1u), C);
+  BB_CUDA(h, launch_merge_emit(P, k, rescore, static_cast<const float*>(w->q_f32.p), h->cat_f32, false, nullptr, nullptr, &C, stream));
+  h->launches++;
+  int n_mine = B - h->comm_rank * slice;
+  if (n_mine > slice) n_mine = slice;
+  if (n_mine < 0) n_mine = 0;
+  h->comm_expected[C.parity] += static_cast<unsigned long long>(n_mine) * world;
+  h->pending_scatter = true;
+  h->pending_slice = slice;
+  h->pending_parity = C.parity;
+  h->pending_mine = n_mine;
+  h->pending_k = k;
+  h->pending_l2 = (q->flags & BB_Q_SCORES_AS_L2) != 0;
   return BB_OK;
+}
+
+// Second half: wait (on the device, bounded) until every rank's keys of this rank's query slice have arrived, merge
+// the `world` lists per query and emit [n_mine x k].  out_* host or device memory.
+int bb_sharded_collect(bb_handle* h, float* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = device_guard(h);
+  if (rc != BB_OK) return rc;
+  if (!h->pending_scatter) return fail(h, BB_ERR_STATE, "bb_sharded_collect without bb_sharded_scatter");
+  if (out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  Workspace* w = get_ws(h, stream);
+  if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
+  std::lock_guard<std::mutex> g(w->mu);
+  h->pending_scatter = false;
+  const int n_mine = h->pending_mine, k = h->pending_k;
+  const size_t n = static_cast<size_t>(n_mine > 0 ? n_mine : 1) * k;
+  OutPack o;
+  rc = out_prepare(h, w, n, out_scores, out_ids, o);
+  if (rc != BB_OK) return rc;
+  CommParams C;
+  comm_params(h, h->pending_slice, h->pending_parity, C);
+  BB_CUDA(h, launch_merge_inbox(C, n_mine, k, h->comm_expected[C.parity], h->pending_l2, o.d_scores, o.d_ids, w->err_flag(), stream));
+  h->launches++;
+  if (n_mine == 0) return o.host ? check_device_flag(h, w, stream) : defer_flag_check(h, w, stream);
+  return out_finish(h, w, static_cast<size_t>(n_mine) * k, out_scores, out_ids, o, stream);
+}
+
+int bb_search_sharded(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {
+  if (h == nullptr) return BB_ERR_INVALID;
+  if (h->comm_world <= 1) return bb_search(h, q, k, out_scores, out_ids, stream_);   // one rank owns every row and every query
+  if (out_scores == nullptr || out_ids == nullptr) return fail(h, BB_ERR_INVALID, "NULL argument");
+  int rc = bb_sharded_scatter(h, q, k, stream_);
+  if (rc != BB_OK) return rc;
+  return bb_sharded_collect(h, out_scores, out_ids, stream_);
 }
 
 int bb_debug_scores(bb_handle* h, const bb_query_batch* q, float* out_scores, void* stream_) {
@@ -959,7 +1307,7 @@ int bb_debug_scores(bb_handle* h, const bb_query_batch* q, float* out_scores, vo
   }
   ScanParams P;
   Plan plan;
-  rc = run_scan(h, w, q, 32, d, stream, P, plan);
+  rc = run_scan(h, w, q, 32, d, stream, P, plan, false);
   if (rc != BB_OK) return rc;
   if (!dev) BB_CUDA(h, cudaMemcpyAsync(out_scores, d, bytes, cudaMemcpyDeviceToHost, stream));
   return check_device_flag(h, w, stream);
@@ -977,11 +1325,12 @@ int bb_apply_constraints(bb_handle* h, const bb_constraint* constraints, int32_t
   if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const int64_t words = (h->cfg.n_items + 31) / 32;
-  Stager st{h, &w->stage, 0, stream, 0};
+  Stager st{h, w, stream};
   st.account(constraints, sizeof(bb_constraint) * n);
-  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  BB_CUDA(h, st.prepare());
   const void* d_cons;
   BB_CUDA(h, st.get(constraints, sizeof(bb_constraint) * n, &d_cons));
+  BB_CUDA(h, st.flush());
   const bool b_dev = is_device_ptr(out_bitmaps);
   const size_t bm_bytes = sizeof(uint32_t) * static_cast<size_t>(n) * words;
   BB_CUDA(h, w->misc.ensure((b_dev ? 0 : align256(bm_bytes)) + sizeof(unsigned long long) * n + 256));
@@ -1024,16 +1373,17 @@ int bb_hybrid_combine(bb_handle* h, int32_t n_rows, int32_t len_c, const int32_t
   Workspace* w = get_ws(h, stream);
   if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
-  Stager st{h, &w->stage, 0, stream, 0};
+  Stager st{h, w, stream};
   const size_t nc = static_cast<size_t>(n_rows) * len_c, nf = static_cast<size_t>(n_rows) * len_f;
   const size_t nw = weights_per_row ? static_cast<size_t>(n_rows) * 2 : 2;
   st.account(c_ids, 4 * nc); st.account(c_scores, 4 * nc); st.account(f_ids, 4 * nf); st.account(f_scores, 4 * nf);
   st.account(weights, 8 * nw);
-  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  BB_CUDA(h, st.prepare());
   const void *dci, *dcs, *dfi, *dfs, *dw;
   BB_CUDA(h, st.get(c_ids, 4 * nc, &dci)); BB_CUDA(h, st.get(c_scores, 4 * nc, &dcs));
   BB_CUDA(h, st.get(f_ids, 4 * nf, &dfi)); BB_CUDA(h, st.get(f_scores, 4 * nf, &dfs));
   BB_CUDA(h, st.get(weights, 8 * nw, &dw));
+  BB_CUDA(h, st.flush());
   const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
   const size_t so = align256(sizeof(double) * static_cast<size_t>(n_rows) * k);
   BB_CUDA(h, w->misc.ensure(so + sizeof(int32_t) * static_cast<size_t>(n_rows) * k + 256));
@@ -1061,11 +1411,12 @@ int bb_merge_topk(bb_handle* h, int32_t n_queries, int32_t n_lists, int32_t len,
   if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
   const size_t n_in = static_cast<size_t>(n_lists) * n_queries * len;
-  Stager st{h, &w->stage, 0, stream, 0};
+  Stager st{h, w, stream};
   st.account(scores, 4 * n_in); st.account(ids, 4 * n_in);
-  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  BB_CUDA(h, st.prepare());
   const void *ds, *di;
   BB_CUDA(h, st.get(scores, 4 * n_in, &ds)); BB_CUDA(h, st.get(ids, 4 * n_in, &di));
+  BB_CUDA(h, st.flush());
   const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);
   const size_t n_out = static_cast<size_t>(n_queries) * k;
   if (!s_dev) BB_CUDA(h, w->out_scores.ensure(4 * n_out));
@@ -1112,13 +1463,14 @@ int bb_item_item_topk(bb_handle* h, int64_t n_users, int32_t n_items, const int6
   if (is_device_ptr(indptr)) BB_CUDA(h, cudaMemcpy(&nnz, indptr + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost));
   else nnz = indptr[n_users];
   if (nnz < 0) return fail(h, BB_ERR_INVALID, "negative nnz");
-  Stager st{h, &w->stage, 0, stream, 0};
+  Stager st{h, w, stream};
   st.account(indptr, 8 * static_cast<size_t>(n_users + 1)); st.account(indices, 4 * static_cast<size_t>(nnz)); st.account(values, 4 * static_cast<size_t>(nnz));
-  BB_CUDA(h, w->stage.ensure(st.need + 256));
+  BB_CUDA(h, st.prepare());
   const void *dp, *di, *dv;
   BB_CUDA(h, st.get(indptr, 8 * static_cast<size_t>(n_users + 1), &dp));
   BB_CUDA(h, st.get(indices, 4 * static_cast<size_t>(nnz), &di));
   BB_CUDA(h, st.get(values, 4 * static_cast<size_t>(nnz), &dv));
+  BB_CUDA(h, st.flush());
   const size_t ws_bytes = item_item_workspace_bytes(n_users, n_items, nnz);
   BB_CUDA(h, w->misc.ensure(ws_bytes));
   const bool s_dev = is_device_ptr(out_scores), i_dev = is_device_ptr(out_ids);

@@ -28,7 +28,7 @@ prep_catalog_kernel(const float* __restrict__ emb, const float* __restrict__ cf,
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
   float inv_norm_den = 1.f;
-  if (dim > 0 && metric == BB_METRIC_COSINE) {
+  if (dim > 0 && emb != nullptr && metric == BB_METRIC_COSINE) {
     float ss = 0.f;
     for (int c = lane; c < dim; c += 32) {
       const float x = __ldg(emb + row * dim + c);
@@ -38,10 +38,11 @@ prep_catalog_kernel(const float* __restrict__ emb, const float* __restrict__ cf,
     const float nrm = sqrtf(ss);
     inv_norm_den = (nrm == 0.f) ? 1.f : nrm;
   }
-  for (int c = lane; c < k_pad; c += 32) {
+  // emb == nullptr with dim > 0: factor-only reload (re-trained CF factors) -- the embedding columns are kept
+  for (int c = (emb == nullptr ? dim : 0) + lane; c < k_pad; c += 32) {
     float x = 0.f;
     if (c < dim) x = __fdiv_rn(__ldg(emb + row * dim + c), inv_norm_den);
-    else if (c < dim + cf_dim) x = __ldg(cf + row * cf_dim + (c - dim));
+    else if (c < dim + cf_dim && cf != nullptr) x = __ldg(cf + row * cf_dim + (c - dim));
     if (out_f32 != nullptr) out_f32[row * k_pad + c] = x;
     if (out_bf16 != nullptr) out_bf16[row * k_pad + c] = __float2bfloat16_rn(x);
   }
@@ -53,12 +54,19 @@ prep_catalog_kernel(const float* __restrict__ emb, const float* __restrict__ cf,
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ q_emb, const int32_t* __restrict__ q_item, const float* __restrict__ q_cf,
                     const float* __restrict__ w_c, const float* __restrict__ w_f, float w_c_all, float w_f_all,
-                    int n_queries, int dim, int cf_dim, int k_pad, int metric, const float* __restrict__ cat_f32,
+                    int n_queries, int b_pad, int dim, int cf_dim, int k_pad, int metric, const float* __restrict__ cat_f32,
                     const __nv_bfloat16* __restrict__ cat_bf16, int64_t id_offset, int64_t n_items,
                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int32_t* err_flag) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= n_queries) return;
+  if (row >= b_pad) return;
+  if (row >= n_queries) {                     // padding rows of the last query block: zero operands
+    for (int c = lane; c < k_pad; c += 32) {
+      out_f32[static_cast<int64_t>(row) * k_pad + c] = 0.f;
+      out_bf16[static_cast<int64_t>(row) * k_pad + c] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
   const float wc = w_c != nullptr ? __ldg(w_c + row) : w_c_all;
   const float wf = w_f != nullptr ? __ldg(w_f + row) : w_f_all;
   int64_t src_item = -1;
@@ -124,27 +132,37 @@ __global__ void gather_rows_kernel(const float* __restrict__ cat_f32, const __nv
 }
 
 // ------------------------------------------------------------------ K3: constraint mask
-// grid.y = constraint; each warp produces 32-bit words of the bitmap (lane = item).
-// Algorithmic bytes: 8 B metadata read + 1/8 B written per item per constraint.
+// One pass over the metadata for ALL constraints of the launch (<= kMaskCons, descriptors in shared memory): a warp
+// handles 32 items per step (lane = item, one 8-byte metadata read), evaluates every descriptor on the registers and
+// lane c keeps the ballot word of constraint c, so a step ends with one store per constraint.
+// Algorithmic bytes: 8 B metadata read per item + 1/8 B written per item per constraint.
+constexpr int kMaskCons = 32;
 __global__ void __launch_bounds__(256)
-mask_kernel(const ScanParams P, uint32_t* __restrict__ out_bitmaps, unsigned long long* __restrict__ out_counts) {
+mask_kernel(const ScanParams P, int c_begin, int n_cons, uint32_t* __restrict__ out_bitmaps,
+            unsigned long long* __restrict__ out_counts) {
+  __shared__ bb_constraint s_cons[kMaskCons];
+  for (int i = threadIdx.x; i < n_cons; i += blockDim.x) s_cons[i] = P.cons[c_begin + i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int c_idx = blockIdx.y;
-  const bb_constraint c = P.cons[c_idx];
   const int64_t n_words = (P.n_items + 31) >> 5;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  unsigned long long count = 0;
+  unsigned long long count = 0;                  // lane c: valid items of constraint c seen by this warp
   for (int64_t w = warp0; w < n_words; w += n_warps) {
     const int64_t item = (w << 5) + lane;
-    const bool ok = item < P.n_items && constraint_ok(P, c, item);
-    const unsigned bits = __ballot_sync(kFull, ok);
-    if (lane == 0) {
-      out_bitmaps[static_cast<int64_t>(c_idx) * n_words + w] = bits;
-      count += __popc(bits);
+    const bool in = item < P.n_items;
+    const int2 m = in ? __ldg(P.meta + item) : make_int2(0, 0);
+    unsigned mine = 0u;
+    for (int c = 0; c < n_cons; ++c) {
+      const unsigned bits = __ballot_sync(kFull, in && constraint_ok_meta(P, s_cons[c], item, m));
+      if (lane == c) mine = bits;
+    }
+    if (lane < n_cons) {
+      out_bitmaps[static_cast<int64_t>(c_begin + lane) * n_words + w] = mine;
+      count += __popc(mine);
     }
   }
-  if (lane == 0 && count) atomicAdd(out_counts + c_idx, count);
+  if (lane < n_cons && count) atomicAdd(out_counts + c_begin + lane, count);
 }
 
 // ------------------------------------------------------------------ running top-k' merger (one warp)
@@ -220,10 +238,11 @@ struct WarpMerger {
 // candidates that are still >= the final shared threshold and keep the best k_sel.
 // Phase 2 (all warps, optional): exact fp32 re-score of the survivors against the
 // fp32 operand copy (gather of k_sel rows of k_pad floats).  Phase 3: final sort, emit.
+template <bool kScatter>
 __global__ void __launch_bounds__(128)
 merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restrict__ q_f32,
                   const float* __restrict__ cat_f32, int as_l2, float* __restrict__ out_scores,
-                  int32_t* __restrict__ out_ids) {
+                  int32_t* __restrict__ out_ids, const __grid_constant__ CommParams C) {
   __shared__ uint64_t stage_all[4][kCap];
   uint64_t* stage = stage_all[0];
   const int q = blockIdx.x;
@@ -309,6 +328,17 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     __syncthreads();
   }
 
+  if constexpr (kScatter) {
+    // row-sharded catalog: this rank's k best keys of query q go straight into the OWNER's inbox (peer stores over
+    // NVLink when the owner is another GPU), then one arrival is counted there
+    const int owner = q / C.slice;
+    unsigned long long* dst = C.inbox[owner] + inbox_offset(C, C.parity, C.rank, q - owner * C.slice);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = stage[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd_system(C.arrivals[owner] + C.parity, 1ull);
+    return;
+  }
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const uint64_t key = stage[i];
     float s = -INFINITY;
@@ -322,6 +352,140 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     }
     out_scores[static_cast<int64_t>(q) * k + i] = s;
     out_ids[static_cast<int64_t>(q) * k + i] = id;
+  }
+}
+
+// ------------------------------------------------------------------ owner-side merge of a collective search
+// One warp per query of this rank's slice: wait until every rank's keys of the slice have arrived (cumulative
+// counter, bounded wait), merge the `world` lists, emit.
+__global__ void __launch_bounds__(128)
+merge_inbox_kernel(const __grid_constant__ CommParams C, int n_mine, int k, unsigned long long expected, int as_l2,
+                   float* __restrict__ out_scores, int32_t* __restrict__ out_ids, int32_t* err_flag) {
+  __shared__ uint64_t stage_all[4][kCap];
+  __shared__ int s_ok;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    const unsigned long long* cnt = C.arrivals[C.rank] + C.parity;
+    int ok = 1;
+    const long long t0 = clock64();
+    while (true) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(cnt) : "memory");
+      if (v >= expected) break;
+      __nanosleep(500);
+      if (clock64() - t0 > 6000000000ll) {        // ~3 s: a peer died; fail the call instead of hanging the GPU
+        atomicExch(err_flag, 108);
+        ok = 0;
+        break;
+      }
+    }
+    s_ok = ok;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const int q = blockIdx.x * 4 + warp;
+  if (q >= n_mine) return;
+  uint64_t* stage = stage_all[warp];
+  WarpMerger mg;
+  mg.init(stage, lane);
+  for (int r = 0; r < C.world; ++r) {
+    const unsigned long long* src = C.inbox[C.rank] + inbox_offset(C, C.parity, r, q);
+    for (int i = 0; i < k; i += 32) mg.offer(i + lane < k ? __ldcg(src + i + lane) : 0ull);
+  }
+  mg.flush();
+  for (int i = lane; i < k; i += 32) {
+    const uint64_t key = stage[i];
+    float s = key ? key_score(key) : -INFINITY;
+    if (as_l2) s = key ? 2.f - 2.f * s : INFINITY;
+    out_scores[static_cast<int64_t>(q) * k + i] = s;
+    out_ids[static_cast<int64_t>(q) * k + i] = key ? key_id(key) : -1;
+  }
+}
+
+// ------------------------------------------------------------------ threshold seeding from the pilot pass
+// One warp per query row: the pilot pass left the row's best valid score of every 8-column group of the leading
+// pilot_items rows.  Group maxima are scores of DISTINCT valid items, except that the query's own exclusion lists were
+// not applied: with E listed ids inside the pilot range, the (m + E)-th largest maximum is a lower bound of the row's
+// m-th best valid score.  m = k' seeds the threshold word, m = k'/8, k'/4, k'/2 this rank's level claims.
+struct WarpMerger32 {
+  uint32_t* stage;     // [256]: [0,128) sorted best so far, [128,256) new
+  int n_new, lane;
+  uint32_t floor_key;
+  __device__ void init(uint32_t* s, int l) {
+    stage = s; n_new = 0; lane = l; floor_key = 0u;
+    for (int i = lane; i < 256; i += 32) stage[i] = 0u;
+    __syncwarp();
+  }
+  __device__ void flush() {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = stage[(i << 5) | lane];
+    __syncwarp();
+    warp_sort_desc<8, uint32_t>(v, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) stage[(i << 5) | lane] = (i < 4) ? v[i] : 0u;
+    floor_key = __shfl_sync(kFull, v[3], 31);
+    n_new = 0;
+    __syncwarp();
+  }
+  __device__ void offer(uint32_t key) {
+    if (key <= floor_key) key = 0u;
+    const unsigned m = __ballot_sync(kFull, key != 0u);
+    if (m == 0) return;
+    if (key != 0u) stage[128 + n_new + __popc(m & ((1u << lane) - 1u))] = key;
+    n_new += __popc(m);
+    __syncwarp();
+    if (n_new + 32 > 128) flush();
+  }
+};
+
+__device__ __forceinline__ int64_t lower_bound_ids(const int32_t* ids, int64_t lo, int64_t hi, int64_t gid) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (static_cast<int64_t>(__ldg(ids + mid)) < gid) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128)
+seed_thresholds_kernel(const ScanParams P, int64_t pilot_items) {
+  __shared__ uint32_t stage_all[4][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= P.n_queries) return;
+  WarpMerger32 mg;
+  mg.init(stage_all[warp], lane);
+  const float* src = P.pilot_max + static_cast<int64_t>(row) * P.pilot_groups;
+  for (int g = 0; g < P.pilot_groups; g += 32) {
+    uint32_t key = 0u;
+    if (g + lane < P.pilot_groups) {
+      key = f2ord(__ldcg(src + g + lane));
+      if (key <= kOrdNegInf) key = 0u;          // (no valid item in the group)
+    }
+    mg.offer(key);
+  }
+  mg.flush();
+  // listed ids inside the pilot range (they may sit behind up to E of the maxima)
+  int64_t excl = 0;
+  if (lane == 0 && P.q_excl_n > 0) {
+    for (int e = 0; e < P.q_excl_n; ++e) {
+      const int32_t l = __ldg(P.q_excl + static_cast<int64_t>(row) * P.q_excl_n + e);
+      if (l < 0) continue;
+      const int64_t lo = __ldg(P.excl_off + l), hi = __ldg(P.excl_off + l + 1);
+      excl += lower_bound_ids(P.excl_ids, lo, hi, P.id_offset + pilot_items) - lower_bound_ids(P.excl_ids, lo, hi, P.id_offset);
+    }
+  }
+  excl = __shfl_sync(kFull, excl, 0);
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      if (l < 3 && P.lvl_stride == 0) continue;
+      const int64_t e = (P.k_sel >> (3 - l)) + excl - 1;
+      if (e >= 128) continue;
+      const uint32_t v = mg.stage[e];
+      if (v <= kOrdNegInf) continue;
+      if (l == 3) thr_raise(P, row, v); else lvl_raise(P, row, l, v);
+    }
   }
 }
 
@@ -431,12 +595,12 @@ cudaError_t launch_prep_catalog(const float* emb, const float* cf, int64_t n_row
 }
 
 cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const float* q_cf, const float* w_c,
-                                const float* w_f, float w_c_all, float w_f_all, int n_queries, int dim, int cf_dim,
+                                const float* w_f, float w_c_all, float w_f_all, int n_queries, int b_pad, int dim, int cf_dim,
                                 int k_pad, int metric, const float* cat_f32, const void* cat_bf16, int64_t id_offset,
                                 int64_t n_items, float* out_f32, void* out_bf16, int32_t* err_flag,
                                 cudaStream_t stream) {
-  prep_queries_kernel<<<blocks_for(n_queries, 8), 256, 0, stream>>>(
-      q_emb, q_item, q_cf, w_c, w_f, w_c_all, w_f_all, n_queries, dim, cf_dim, k_pad, metric, cat_f32,
+  prep_queries_kernel<<<blocks_for(b_pad, 8), 256, 0, stream>>>(
+      q_emb, q_item, q_cf, w_c, w_f, w_c_all, w_f_all, n_queries, b_pad, dim, cf_dim, k_pad, metric, cat_f32,
       static_cast<const __nv_bfloat16*>(cat_bf16), id_offset, n_items, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
       err_flag);
   return cudaGetLastError();
@@ -464,14 +628,35 @@ cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bi
   int bx = static_cast<int>((n_words + 7) / 8);
   if (bx > 148 * 8) bx = 148 * 8;       // grid-stride: 8 resident CTAs per SM
   if (bx < 1) bx = 1;
-  mask_kernel<<<dim3(bx, n_constraints), 256, 0, stream>>>(P, out_bitmaps, out_counts);
+  for (int c0 = 0; c0 < n_constraints; c0 += kMaskCons) {
+    const int n = n_constraints - c0 < kMaskCons ? n_constraints - c0 : kMaskCons;
+    mask_kernel<<<bx, 256, 0, stream>>>(P, c0, n, out_bitmaps, out_counts);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_merge_emit(const ScanParams& P, int k, bool rescore, const float* q_f32, const float* cat_f32,
-                              bool as_l2, float* out_scores, int32_t* out_ids, cudaStream_t stream) {
-  merge_emit_kernel<<<P.n_queries, 128, 0, stream>>>(P, k, rescore ? 1 : 0, q_f32, cat_f32, as_l2 ? 1 : 0, out_scores,
-                                                     out_ids);
+                              bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream) {
+  if (comm != nullptr) {
+    merge_emit_kernel<true><<<P.n_queries, 128, 0, stream>>>(P, k, rescore ? 1 : 0, q_f32, cat_f32, 0, nullptr, nullptr, *comm);
+  } else {
+    CommParams none{};
+    merge_emit_kernel<false><<<P.n_queries, 128, 0, stream>>>(P, k, rescore ? 1 : 0, q_f32, cat_f32, as_l2 ? 1 : 0, out_scores,
+                                                              out_ids, none);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_inbox(const CommParams& comm, int n_mine, int k, unsigned long long expected, bool as_l2,
+                               float* out_scores, int32_t* out_ids, int32_t* err_flag, cudaStream_t stream) {
+  if (n_mine <= 0) return cudaSuccess;
+  merge_inbox_kernel<<<blocks_for(n_mine, 4), 128, 0, stream>>>(comm, n_mine, k, expected, as_l2 ? 1 : 0, out_scores, out_ids,
+                                                                err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seed_thresholds(const ScanParams& P, int64_t pilot_items, cudaStream_t stream) {
+  seed_thresholds_kernel<<<blocks_for(P.n_queries, 4), 128, 0, stream>>>(P, pilot_items);
   return cudaGetLastError();
 }
 

@@ -131,6 +131,8 @@ struct ScanParams {
   const int64_t* excl_off;
   const int32_t* excl_ids;
   const int32_t* cons_index;      // per-row index into cons[] (distinct constraint sets) or nullptr
+  const int32_t* q_excl;          // per-QUERY exclusion-list indices [n_queries x q_excl_n] (-1 none): the user's rated items
+  int32_t q_excl_n;               // 0..3
   const uint32_t* class_valid;    // per distinct constraint set: validity bitmap over local rows (mask kernel) or nullptr
   int64_t class_words;            // words per class bitmap
   // candidate buffers: slot = (split * n_sub + sub) * b_pad + row; cand[slot * cap + i], cnt[slot]
@@ -144,17 +146,29 @@ struct ScanParams {
   // local k'-th best is a valid lower bound of the GLOBAL k'-th best, so every shard may prune with it.  Words of
   // another epoch (an earlier search, a rank that runs ahead) are ignored by readers and lose every atomicMax.
   unsigned long long* thr_g;
-  unsigned long long* peer_thr[7];   // the same array on the peer GPUs (cudaIpc mappings)
+  // Union thresholds of a row-sharded catalog (collective searches).  Besides thr_g every rank keeps three LEVEL words
+  // per row, same (epoch | ordered score) encoding, at thr_g + (1 + l) * lvl_stride + row, l = 0..2: "this rank holds at
+  // least k_sel >> (3 - l) valid candidates with score >= value" (raised at every compaction from the stream's sorted
+  // prefix).  If `need` ranks each hold >= m candidates >= T and need * m >= k_sel then T is a lower bound of the
+  // GLOBAL k_sel-th best: the scan's poller warp reads the peers' words through NVLink peer memory (plain loads, no
+  // remote atomics), takes for each level the (8 >> l)-th largest claim over the ranks and raises the LOCAL thr_g.
+  // thr_g itself holds bounds that are valid globally, so the max over all ranks' thr_g words is taken as well.
+  const unsigned long long* peer_thr[7];   // the same block on the peer GPUs (cudaIpc / peer mappings), read-only here
   int32_t n_peers;
+  int64_t lvl_stride;                // 0 = private search (no level words)
   uint32_t epoch;
+  // pilot pass (threshold seeding): the epilogue writes, per row, the maximum VALID score of every group of 8 columns of
+  // the leading pilot tiles to pilot_max[row * pilot_groups + g] instead of collecting candidates
+  float* pilot_max;
+  int32_t pilot_groups;
+  int32_t pilot_mode;                // 1 = this launch is the pilot pass
   // schedule
   int32_t n_qblocks;      // query blocks
-  int32_t n_splits;       // catalog splits of the tiles after the pilot (regular units = n_qblocks * n_splits)
-  int32_t n_tiles;        // catalog tiles of tile_items rows
+  int32_t n_splits;       // catalog splits (units = n_qblocks * n_splits)
+  int32_t n_tiles;        // catalog tiles of tile_items rows covered by this launch (the pilot pass covers the leading ones only)
   int32_t tile_items;
-  int32_t pilot_tiles;    // leading tiles scanned by ONE unit per query block before everything else (0 = none)
-  int32_t n_slot_splits;  // n_splits (+1 when there is a pilot): candidate-buffer rows per (sub, query)
-  int32_t n_units;        // unit indices to walk (pilot wave incl. idle slots + regular units)
+  int32_t n_slot_splits;  // candidate-buffer rows per (sub, query) = n_splits of the main scan
+  int32_t n_units;        // unit indices to walk
   // debug
   float* dump;            // dense [b x n_items] score dump (bb_debug_scores) or nullptr
   unsigned long long* stat_candidates;
@@ -165,37 +179,40 @@ struct ScanParams {
 };
 
 __device__ __forceinline__ void split_tile_range(const ScanParams& P, int split, int& t0, int& t1) {
-  const int64_t n = P.n_tiles - P.pilot_tiles;
-  t0 = P.pilot_tiles + static_cast<int>((n * split) / P.n_splits);
-  t1 = P.pilot_tiles + static_cast<int>((n * (split + 1)) / P.n_splits);
+  const int64_t n = P.n_tiles;
+  t0 = static_cast<int>((n * split) / P.n_splits);
+  t1 = static_cast<int>((n * (split + 1)) / P.n_splits);
 }
 
-// Work unit u -> (query block, candidate-slot row, tile range).  With a pilot, the first wave holds one short unit
-// per query block over the leading tiles (all other CTA groups idle for those few microseconds): every stream of
-// the following waves then starts from a threshold instead of cold.
+// Work unit u -> (query block, candidate-slot row, tile range); units are split-major so that the query blocks of a
+// split stream the same catalog region at the same time.
 struct UnitInfo {
   int qb, split_slot, t0, t1;
-  bool valid;
 };
-__device__ __forceinline__ UnitInfo decode_unit(const ScanParams& P, int u, int n_groups) {
+__device__ __forceinline__ UnitInfo decode_unit(const ScanParams& P, int u) {
   UnitInfo r;
-  if (P.pilot_tiles > 0) {
-    const int n_pilot_slots = ((P.n_qblocks + n_groups - 1) / n_groups) * n_groups;
-    if (u < n_pilot_slots) {
-      r.valid = u < P.n_qblocks;
-      r.qb = u;
-      r.split_slot = P.n_splits;
-      r.t0 = 0;
-      r.t1 = P.pilot_tiles;
-      return r;
-    }
-    u -= n_pilot_slots;
-  }
-  r.valid = true;
   r.qb = u % P.n_qblocks;
   r.split_slot = u / P.n_qblocks;
   split_tile_range(P, r.split_slot, r.t0, r.t1);
   return r;
+}
+
+// ---------------------------------------------------------------- candidate exchange of a row-sharded catalog
+// Every rank exports one block of device memory (cudaIpc / peer access): threshold + level words, arrival counters and
+// an inbox.  Query q of a collective search is OWNED by rank q / slice; after its local merge every rank stores its k
+// final keys of q straight into the owner's inbox (peer stores over NVLink, fused into merge_emit) and bumps the
+// owner's arrival counter; the owner merges the `world` lists of its slice.  Two inbox halves (search parity): a rank
+// can be at most one collective search ahead of a peer.
+struct CommParams {
+  unsigned long long* inbox[8];      // per rank: inbox base, [2 parities][8 senders][slice_cap][k_cap] keys
+  unsigned long long* arrivals[8];   // per rank: [2] cumulative arrival counters
+  int32_t rank, world;
+  int32_t slice;                     // queries per owner = ceil(n_queries / world)
+  int32_t slice_cap, k_cap;          // inbox geometry (fixed at creation)
+  int32_t parity;
+};
+__device__ __forceinline__ int64_t inbox_offset(const CommParams& C, int parity, int sender, int local_q) {
+  return ((static_cast<int64_t>(parity) * 8 + sender) * C.slice_cap + local_q) * C.k_cap;
 }
 
 // ---------------------------------------------------------------- shared threshold words
@@ -205,10 +222,12 @@ __device__ __forceinline__ uint32_t thr_load(const ScanParams& P, int row) {
 }
 __device__ __forceinline__ void thr_raise(const ScanParams& P, int row, uint32_t ord) {
   const unsigned long long v = (static_cast<unsigned long long>(P.epoch) << 32) | ord;
-  atomicMax(P.thr_g + row, v);
-#pragma unroll
-  for (int p = 0; p < 7; ++p)                       // (constant indices: a run-time index would copy the kernel parameters to local memory)
-    if (p < P.n_peers) atomicMax_system(P.peer_thr[p] + row, v);   // fire-and-forget over NVLink
+  atomicMax(P.thr_g + row, v);        // local only: peers PULL these words (poller warp of the tcgen05 scan)
+}
+// level claim l (0..2) of this rank for `row`: at least k_sel >> (3 - l) candidates score >= ord
+__device__ __forceinline__ void lvl_raise(const ScanParams& P, int row, int l, uint32_t ord) {
+  const unsigned long long v = (static_cast<unsigned long long>(P.epoch) << 32) | ord;
+  atomicMax(P.thr_g + (1 + l) * P.lvl_stride + row, v);
 }
 
 // ---------------------------------------------------------------- hard-constraint predicate
@@ -228,9 +247,8 @@ __device__ __forceinline__ bool list_contains(const int32_t* ids, int64_t lo, in
 
 // Integer restatement of the reference's constraint SQL (hard_constraint_filter.py:318-480)
 // evaluated for one (query row, local item).
-__device__ __forceinline__ bool constraint_ok(const ScanParams& P, const bb_constraint& c, int64_t item) {
+__device__ __forceinline__ bool constraint_ok_meta(const ScanParams& P, const bb_constraint& c, int64_t item, const int2 m) {
   if (c.flags & BB_C_ALWAYS_FALSE) return false;
-  const int2 m = __ldg(P.meta + item);
   const int32_t parts = m.x;
   const int32_t year = static_cast<int16_t>(m.y & 0xffff);
   const int32_t theme = m.y >> 16;                 // arithmetic shift: -1 stays -1 (SQL NULL)
@@ -251,11 +269,26 @@ __device__ __forceinline__ bool constraint_ok(const ScanParams& P, const bb_cons
   }
   return true;
 }
+__device__ __forceinline__ bool constraint_ok(const ScanParams& P, const bb_constraint& c, int64_t item) {
+  if (c.flags & BB_C_ALWAYS_FALSE) return false;
+  return constraint_ok_meta(P, c, item, __ldg(P.meta + item));
+}
+
+// The query's own exclusion lists (already-rated items, recommendation_system.py:441-451).
+__device__ __forceinline__ bool query_excluded(const ScanParams& P, int row, int64_t item) {
+  const int32_t gid = static_cast<int32_t>(item + P.id_offset);
+  for (int e = 0; e < P.q_excl_n; ++e) {
+    const int32_t l = __ldg(P.q_excl + static_cast<int64_t>(row) * P.q_excl_n + e);
+    if (l >= 0 && list_contains(P.excl_ids, __ldg(P.excl_off + l), __ldg(P.excl_off + l + 1), gid)) return true;
+  }
+  return false;
+}
 
 // Validity of local `item` for query `row` (bounds, self exclusion, constraints).
 static __device__ __noinline__ bool item_ok(const ScanParams& P, int row, int64_t item) {
   if (item >= P.n_items) return false;
   if (P.self_id != nullptr && __ldg(P.self_id + row) == static_cast<int32_t>(item + P.id_offset)) return false;
+  if (P.q_excl_n > 0 && query_excluded(P, row, item)) return false;
   if (P.cons == nullptr) return true;
   const int64_t ci = P.cons_index != nullptr ? __ldg(P.cons_index + row) : static_cast<int64_t>(row) * P.cons_stride;
   const bb_constraint c = P.cons[ci];
@@ -364,9 +397,13 @@ __device__ __forceinline__ int warp_compact(uint64_t* buf, int cnt, int k_sel, i
 // stream's own threshold).  This lets ~74 streams per row share a threshold close to the global one instead of
 // the max of their local ones.
 constexpr int kRefineSlots = 128;
-__device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, int row, int lane) {
+// best[3] = bound of the row's k'-th best (0 = none).  Collective searches (P.lvl_stride > 0) also derive the rank's
+// LEVEL claims best[l], l = 0..2 ("this rank holds >= k' >> (3 - l) candidates >= best[l]"): if j streams each hold >= r
+// keys >= T the rank holds >= j * r of them, so level m takes the ceil(m / r)-th largest of the streams' r-th best keys.
+__device__ __forceinline__ void warp_refine_threshold(const ScanParams& P, int row, int lane, uint32_t (&best)[4]) {
+  best[0] = best[1] = best[2] = best[3] = 0u;
   const int n_slots = P.n_slot_splits * P.n_sub;
-  if (n_slots <= 1) return 0u;
+  if (n_slots <= 1) return;
   const int stride = (n_slots + kRefineSlots - 1) / kRefineSlots;
   const int n_use = (n_slots + stride - 1) / stride;
   constexpr int kPer = kRefineSlots / 32;
@@ -385,29 +422,40 @@ __device__ __forceinline__ uint32_t warp_refine_threshold(const ScanParams& P, i
     n_pub += __popc(__ballot_sync(kFull, c[i] > 0));
   }
   __threadfence();                                  // keys read below are at least as new as the counts read above
-  if (n_pub == 0) return 0u;
+  if (n_pub == 0) return;
   int r0 = 2;
   while (r0 < P.k_sel && (P.k_sel + r0 - 1) / r0 > n_pub) r0 <<= 1;
-  uint32_t best = 0u;
+  // private searches: the two useful levels of the k' bound; collective searches start at the smallest r that can
+  // serve the k'/8 claim
+  int r_lo = r0;
+  const bool levels = P.lvl_stride > 0;
+  if (levels) {
+    const int m0 = P.k_sel >> 3;
+    r_lo = 1;
+    while (r_lo < m0 && (m0 + r_lo - 1) / r_lo > n_pub) r_lo <<= 1;
+  }
 #pragma unroll 1
-  for (int l = 0; l < 2; ++l) {
-    const int r = r0 << l;
-    if (r >= P.k_sel) break;                        // the r = k' level is the stream's own threshold
-    const int need = (P.k_sel + r - 1) / r;
+  for (int r = r_lo; r <= 2 * r0 && r <= P.k_sel; r <<= 1) {
     uint32_t v[kPer];
 #pragma unroll
     for (int i = 0; i < kPer; ++i)
       v[i] = (c[i] >= r) ? static_cast<uint32_t>(__ldcg(P.cand + slot[i] * P.cap + (r - 1)) >> 32) : 0u;
     warp_sort_desc<kPer, uint32_t>(v, lane);
-    const int e = need - 1;                         // element e lives in register e>>5 of lane e&31
-    uint32_t t = 0u;
 #pragma unroll
-    for (int i = 0; i < kPer; ++i)
-      if ((e >> 5) == i) t = v[i];
-    t = __shfl_sync(kFull, t, e & 31);
-    best = t > best ? t : best;
+    for (int l = 0; l < 4; ++l) {
+      if (l < 3 && !levels) continue;
+      if (l == 3 && (r < r0 || r >= P.k_sel)) continue;   // (the r = k' level is the stream's own threshold)
+      const int m = P.k_sel >> (3 - l);
+      const int e = (m + r - 1) / r - 1;              // element e lives in register e>>5 of lane e&31
+      if (e >= kRefineSlots) continue;
+      uint32_t t = 0u;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i)
+        if ((e >> 5) == i) t = v[i];
+      t = __shfl_sync(kFull, t, e & 31);
+      best[l] = t > best[l] ? t : best[l];
+    }
   }
-  return best;
 }
 
 // Compacts the buffers of the rows in `need0` (a warp-uniform lane mask; lane l holds row l's RowState): sort /
@@ -440,20 +488,37 @@ __device__ __forceinline__ int warp_compact_rows(const ScanParams& P, RowState& 
     st.sorted = my_nc;
   }
   __syncwarp();
-  // phase 3: cross-stream refinement for the rows that asked for it, then raise the shared threshold
-  uint32_t my_ref = 0u;
+  // phase 3: cross-stream refinement for the rows that asked for it, then raise the shared threshold (and, in
+  // collective searches, this rank's level claims: the stream's own sorted prefix and the refined ones)
+  uint32_t my_ref[4] = {0u, 0u, 0u, 0u};
   for (unsigned need = need0 & refine_mask; need; need &= need - 1) {
     const int src = __ffs(need) - 1;
     const int src_row = __shfl_sync(kFull, row, src);
-    const uint32_t refined = warp_refine_threshold(P, src_row, lane);
-    if (lane == src) my_ref = refined;
+    uint32_t refined[4];
+    warp_refine_threshold(P, src_row, lane, refined);
+    if (lane == src) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) my_ref[l] = refined[l];
+    }
   }
   if (mine) {
     uint32_t o = f2ord(my_nt);
-    o = my_ref > o ? my_ref : o;
+    o = my_ref[3] > o ? my_ref[3] : o;
     if (o > f2ord(st.thr)) {
       st.thr = ord2f(o);
       thr_raise(P, row, o);
+    }
+    if (P.lvl_stride > 0) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        const int m = P.k_sel >> (3 - l);
+        uint32_t claim = my_ref[l];
+        if (my_nc >= m) {
+          const uint32_t own = static_cast<uint32_t>(__ldcg(st.buf + (m - 1)) >> 32);
+          claim = own > claim ? own : claim;
+        }
+        if (claim > kOrdNegInf) lvl_raise(P, row, l, claim);
+      }
     }
   }
   return __popc(need0);

@@ -27,7 +27,7 @@ cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* 
 cudaError_t launch_prep_catalog(const float* emb, const float* cf, int64_t n_rows, int dim, int cf_dim, int k_pad,
                                 int metric, float* out_f32, void* out_bf16, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const float* q_cf, const float* w_c,
-                                const float* w_f, float w_c_all, float w_f_all, int n_queries, int dim, int cf_dim,
+                                const float* w_f, float w_c_all, float w_f_all, int n_queries, int b_pad, int dim, int cf_dim,
                                 int k_pad, int metric, const float* cat_f32, const void* cat_bf16, int64_t id_offset,
                                 int64_t n_items, float* out_f32, void* out_bf16, int32_t* err_flag,
                                 cudaStream_t stream);
@@ -51,8 +51,14 @@ cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bi
                         cudaStream_t stream);
 
 // ---- K4 + K6 merge / re-score / emit (bb_aux.cu)
+// comm != nullptr: collective search of a row-sharded catalog -- the k final keys of every query are stored into the
+// owner rank's inbox (peer memory) instead of out_scores / out_ids
 cudaError_t launch_merge_emit(const ScanParams& P, int k, bool rescore, const float* q_f32, const float* cat_f32,
-                              bool as_l2, float* out_scores, int32_t* out_ids, cudaStream_t stream);
+                              bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream);
+cudaError_t launch_merge_inbox(const CommParams& comm, int n_mine, int k, unsigned long long expected, bool as_l2,
+                               float* out_scores, int32_t* out_ids, int32_t* err_flag, cudaStream_t stream);
+// threshold (and level) seeds from the pilot pass's group maxima (P.pilot_max / P.pilot_groups)
+cudaError_t launch_seed_thresholds(const ScanParams& P, int64_t pilot_items, cudaStream_t stream);
 cudaError_t launch_merge_lists(int n_queries, int n_lists, int len, const float* scores, const int32_t* ids, int k,
                                float* out_scores, int32_t* out_ids, cudaStream_t stream);
 

@@ -14,7 +14,8 @@
 //   * work unit = (query block, catalog split); units are dealt round-robin to groups.
 //
 // Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA),
-// 2 = TMEM allocator, 3 = idle, 4..19 = epilogue (TMEM lane quarter = warp % 4; the four
+// 2 = TMEM allocator, 3 = union-threshold poller (collective searches of a row-sharded catalog: reads the peers' level
+// words over NVLink peer memory; idle otherwise), 4..19 = epilogue (TMEM lane quarter = warp % 4; the four
 // warps of a quarter -- a row group -- split the tile's 256 columns and share ONE candidate
 // stream per (catalog split, query row): row state in shared memory, one named barrier per tile).
 //
@@ -57,9 +58,10 @@ constexpr int kCompactLine = kCapTc - kTcTile;   // a row whose count crosses th
 static_assert(kCompactLine >= kMaxSel, "candidate buffer too small: a compacted row (<= kMaxSel keys) must be below the line");
 static_assert(kTcSubStreams == 1, "one candidate stream per (split, row)");
 constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata of the 32 columns of a chunk
-constexpr int kRowStateBytes = 3 * 128 * 4 + 64;   // per row: count, sorted prefix, threshold; + compaction flags [3 tiles][4 row groups]
+constexpr int kRowStateBytes = 3 * 128 * 4 + 64;   // per row: count, sorted prefix, threshold; + compaction flags [3 tiles][4 row groups] + poller word
 constexpr int kThemeBytes = 32 * 128 * 4;         // per-row allowed-theme bitmaps, word-major [32 words][128 rows]
 constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
+constexpr long long kWaveTimeoutCycles = 40000000ll;  // ~20 ms: the grid is not co-resident, give the wave barrier up
 
 // kRowCons: the batch carries per-row constraint descriptors that are prefiltered in the epilogue (needs the
 // per-row allowed-theme bitmaps in shared memory); otherwise that space is a sixth TMA stage.
@@ -160,6 +162,13 @@ __device__ __forceinline__ void tma_load_2d(const void* tmap, uint32_t bar, uint
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
   }
+}
+
+// peer memory over NVLink: system-scope relaxed load (never served from this SM's L1)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -271,6 +280,50 @@ __device__ __forceinline__ int group_compact(const ScanParams& P, unsigned need,
   return n;
 }
 
+// Union threshold of one query row over the ranks of a row-sharded catalog (see ScanParams::lvl_stride): word 0 of every
+// rank is a bound that is already valid globally (max over ranks), level word l (1..3 in memory, claim "this rank
+// holds >= k' >> (3 - l) candidates >= value") contributes the (8 >> l)-th largest claim over the ranks.  Words of
+// another search epoch count as "no claim".  Raises the LOCAL threshold word only.
+__device__ __forceinline__ void poll_union_threshold(const ScanParams& P, int row) {
+  const uint32_t ep = P.epoch;
+  const int n_ranks = P.n_peers + 1;
+  uint32_t best = 0u, own3 = 0u;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {               // w = 0: thr_g, w = 1..3: level l = w - 1
+    uint32_t v[8];
+    {
+      const unsigned long long x = __ldcg(P.thr_g + w * P.lvl_stride + row);
+      v[0] = (static_cast<uint32_t>(x >> 32) == ep) ? static_cast<uint32_t>(x) : 0u;
+    }
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {             // (constant indices: a run-time index would copy the kernel parameters to local memory)
+      v[1 + p] = 0u;
+      if (p < P.n_peers) {
+        const unsigned long long x = ld_relaxed_sys_u64(P.peer_thr[p] + w * P.lvl_stride + row);
+        v[1 + p] = (static_cast<uint32_t>(x >> 32) == ep) ? static_cast<uint32_t>(x) : 0u;
+      }
+    }
+    if (w == 0) {
+      own3 = v[0];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) best = v[i] > best ? v[i] : best;
+    } else {
+      const int need = 8 >> (w - 1);          // ranks that must hold k' / need candidates each
+      if (need <= n_ranks) {
+        // need-th largest of the claims: the value with exactly need - 1 values ranked before it
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int before = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) before += (v[j] > v[i]) || (v[j] == v[i] && j < i);
+          if (before == need - 1) best = v[i] > best ? v[i] : best;
+        }
+      }
+    }
+  }
+  if (best > own3 && best > kOrdNegInf) atomicMax(P.thr_g + row, (static_cast<unsigned long long>(ep) << 32) | best);
+}
+
 template <int CG, bool kRowCons>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
@@ -296,6 +349,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   int* s_sorted = s_cnt + 128;                                                       // [128] sorted prefix length
   float* s_thr = reinterpret_cast<float*>(s_sorted + 128);                           // [128] row threshold (after compactions)
   unsigned* s_flag = reinterpret_cast<unsigned*>(s_thr + 128);                       // [3][4] rows that crossed the compaction line
+  volatile int* s_poll = reinterpret_cast<volatile int*>(s_flag + 12);               // first query row of this CTA's current unit (-2 not yet, -1 done)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -317,6 +371,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       mbar_init(smem_u32(bar_acc_empty + a), CG * kEpiWarps);
     }
     fence_mbar_init();
+    *s_poll = -2;
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_q);
@@ -335,27 +390,24 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       const uint32_t a_full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_a_full), 0) : smem_u32(bar_a_full);
       int wave = 0;
       for (int u = group; u < n_units; u += n_groups, ++wave) {
-        const UnitInfo ui = decode_unit(P, u, n_groups);
+        const UnitInfo ui = decode_unit(P, u);
         const int qb = ui.qb, t0 = ui.t0, t1 = ui.t1;
         const int row0 = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta;
         // wave barrier: the query blocks that stream the same catalog split share it through L2 only while they
-        // stay in step; do not start wave w before every CTA issued all loads of wave w-1 (all CTAs are
-        // co-resident: the grid never exceeds one CTA per SM)
+        // stay in step; do not start wave w before every CTA issued all loads of wave w-1.  This is a performance
+        // device only: it assumes the whole grid is co-resident (one CTA per SM), which does not hold when another
+        // kernel occupies SMs (a second search on another stream, MPS).  A wait that exceeds kWaveTimeout therefore
+        // BREAKS the barrier for the rest of the launch (the counter jumps past every target) instead of trapping.
         if (wave > 0 && P.wave_counter != nullptr && !(P.debug_flags & 4)) {
-          const uint32_t target = static_cast<uint32_t>(min(wave * n_groups, n_units)) * CG;   // idle pilot slots count too
+          const uint32_t target = static_cast<uint32_t>(min(wave * n_groups, n_units)) * CG;
           const long long t0w = clock64();
           while (*reinterpret_cast<volatile uint32_t*>(P.wave_counter) < target) {
             __nanosleep(200);
-            if (clock64() - t0w > kWatchdogCycles) {
-              if (err != nullptr) atomicExch(err, 107);
-              __threadfence_system();
-              __trap();
+            if (clock64() - t0w > kWaveTimeoutCycles) {
+              atomicMax(P.wave_counter, 0x40000000u);
+              break;
             }
           }
-        }
-        if (!ui.valid) {                               // idle slot of the pilot wave: only take part in the barrier
-          if (P.wave_counter != nullptr) atomicAdd(P.wave_counter, 1u);
-          continue;
         }
         // resident query operand: wait until the previous unit's MMAs stopped reading it
         mbar_wait(smem_u32(bar_a_empty), a_phase ^ 1, err, 101);
@@ -385,8 +437,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       long long t_acc_wait = 0, t_full_wait = 0;     // pipeline triage: who makes the MMA issuer wait
       const long long t_begin = clock64();
       for (int u = group; u < n_units; u += n_groups) {
-        const UnitInfo ui = decode_unit(P, u, n_groups);
-        if (!ui.valid) continue;
+        const UnitInfo ui = decode_unit(P, u);
         const int t0 = ui.t0, t1 = ui.t1;
         const long long tu0 = epi_clock();
         mbar_wait(smem_u32(bar_a_full), a_phase, err, 103);
@@ -437,6 +488,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         atomicAdd(P.stat_candidates + 6, static_cast<unsigned long long>(clock64() - t_begin));
       }
     }
+  } else if (warp == 3) {
+    // ============================== union-threshold poller (collective searches) ==============================
+    if (P.n_peers > 0 && P.lvl_stride > 0 && P.pilot_mode == 0 && P.dump == nullptr) {
+      while (true) {
+        const int base = *s_poll;
+        if (base == -1) break;
+        if (base >= 0) {
+#pragma unroll 1
+          for (int pass = 0; pass < kTcRowsPerCta / 32; ++pass) {
+            const int row = base + pass * 32 + lane;
+            if (row < P.n_queries) poll_union_threshold(P, row);
+          }
+        }
+        // ~40 us between polls (a unit lasts hundreds), in short naps so that the warp leaves promptly at the end
+#pragma unroll 1
+        for (int nap = 0; nap < 20 && *s_poll != -1; ++nap) __nanosleep(2000);
+      }
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ============================== epilogue: mask + running-threshold top-k ==============================
     const int ew = warp & 3;                        // TMEM lane quarter this warp may read
@@ -451,10 +521,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     long long cyc_wait = 0, cyc_slow = 0, cyc_compact = 0, cyc_end = 0, cyc_hold = 0, cyc_ld = 0, t_full = 0;
     const long long cyc_begin = epi_clock();
     for (int u = group; u < n_units; u += n_groups) {
-      const UnitInfo ui = decode_unit(P, u, n_groups);
-      if (!ui.valid) continue;
+      const UnitInfo ui = decode_unit(P, u);
       const int qb = ui.qb, split = ui.split_slot, t0 = ui.t0, t1 = ui.t1;
       const int q = qb * (kTcRowsPerCta * CG) + static_cast<int>(cta_rank) * kTcRowsPerCta + row_in_cta;
+      if (warp == 4 && lane == 0) *s_poll = q;      // (row_in_cta == 0 here: the first row of this CTA's block)
       const bool q_valid = q < P.n_queries;
       // the row's cheap predicates (integer ranges + allowed-theme bitmap) live in registers / smem so that a
       // score that beats the threshold is masked without touching global memory
@@ -466,6 +536,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       if (q_valid && P.self_id != nullptr) {
         const int64_t sl = static_cast<int64_t>(__ldg(P.self_id + q)) - P.id_offset;
         if (sl >= 0 && sl < P.n_items) self_local = sl;
+      }
+      bool excl_only = false;                        // the query's own exclusion lists (rated items) are its only slow predicate
+      if (q_valid && P.q_excl_n > 0) {
+        for (int e = 0; e < P.q_excl_n; ++e) excl_only |= __ldg(P.q_excl + static_cast<int64_t>(q) * P.q_excl_n + e) >= 0;
       }
       const uint32_t* class_row = nullptr;           // this row's constraint-set validity bitmap (class mode)
       if (q_valid && P.cons != nullptr) {
@@ -485,7 +559,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           for (int w = 0; w < 32; ++w) theme_row[w * 128] = (w < P.theme_words) ? __ldg(src + w) : 0u;   // both halves write the same words
         }
       }
-      const bool any_theme = __any_sync(kFull, has_theme);
+      if (needs_full) excl_only = false;             // item_ok() covers the query's lists too
       // ---- one candidate stream per (split, row), shared by the row group's four column-slice warps: count,
       //      sorted-prefix length and threshold live in shared memory, appends take their slot with a shared-memory
       //      atomic; the four warps meet at a named barrier once per tile, where rows that crossed the compaction
@@ -573,6 +647,25 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             continue;
           }
+          if (P.pilot_mode) {
+            // pilot pass: no candidates, only the row's best VALID score of every 8 columns (a group maximum is the score
+            // of one distinct valid item, so the m-th largest of them bounds the row's m-th best from below)
+            unsigned vm = class_word & ~__ballot_sync(kFull, col_item >= P.n_items);
+            const int64_t c0 = item0 + chunk * 32;
+            if (self_local >= c0 && self_local < c0 + 32) vm &= ~(1u << static_cast<int>(self_local - c0));
+            if (dead) vm = 0u;
+            float g[4];
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              float m = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) m = fmaxf(m, ((vm >> (gi * 8 + j)) & 1u) ? __uint_as_float(r[gi * 8 + j]) : -INFINITY);
+              g[gi] = m;
+            }
+            if (q_valid)
+              *reinterpret_cast<float4*>(P.pilot_max + static_cast<int64_t>(q) * P.pilot_groups + (c0 >> 3)) = make_float4(g[0], g[1], g[2], g[3]);
+            continue;
+          }
           // per row: the columns whose score passes the row's threshold and whose item the row's constraint set
           // admits (class mode: one prefetched bitmap word masks the 32 columns; a passing score of a masked-out
           // item must not drag the warp into the slow path -- two thirds of the triggers were of that kind)
@@ -621,7 +714,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                   const float sc = __uint_as_float((j & 1) ? s2[1] : s2[0]);
                   const int64_t item = item0 + chunk * 32 + j;
                   // cheap predicates were applied above; only rows with allow bitmaps / exclusion lists pay the call
-                  if (item != self_local && (!needs_full || item_ok(P, q, item))) {
+                  if (item != self_local && (!needs_full || item_ok(P, q, item)) && (!excl_only || !query_excluded(P, q, item))) {
                     const int pos = atomicAdd(s_cnt + row_in_cta, 1);
                     __stcg(buf + pos, make_key(sc, static_cast<uint32_t>(item + P.id_offset)));
                     if (pos == kCompactLine) atomicOr(s_flag + tslot * 4 + ew, 1u << lane);   // (exactly one append crosses the line)
@@ -633,7 +726,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             cyc_slow += epi_clock() - c0;
           }
         }
-        if (P.dump == nullptr && !(P.debug_flags & 3)) {
+        if (P.dump == nullptr && !(P.debug_flags & 3) && P.pilot_mode == 0) {
           // ---- tile end: every append of this tile by the row group's four warps is complete and visible
           named_bar_sync(bar_id, kColWarps * 32);
           const unsigned need = s_flag[tslot * 4 + ew];          // rows that crossed the line in this tile (written before the barrier)
@@ -649,7 +742,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (++tslot == 3) tslot = 0;
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
-      if (P.dump == nullptr) {
+      if (P.dump == nullptr && P.pilot_mode == 0) {
         // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units
         // that scan this row later start from everything this stream has learnt
         // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
@@ -667,7 +760,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         named_bar_sync(bar_id, kColWarps * 32);                  // the next unit re-initializes the row state
       }
     }
-    if (P.stat_candidates != nullptr && P.dump == nullptr) {
+    if (warp == 4 && lane == 0) *s_poll = -1;       // releases the poller warp
+    if (P.stat_candidates != nullptr && P.dump == nullptr && P.pilot_mode == 0) {
       const unsigned a = __reduce_add_sync(kFull, stat_appends);
       if (lane == 0) {
         atomicAdd(P.stat_candidates + 1, static_cast<unsigned long long>(a));

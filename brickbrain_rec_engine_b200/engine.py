@@ -91,6 +91,7 @@ class ScoringEngine:
         self.n_theme_sets = 0
         self.n_allow = 0
         self.n_excl = 0
+        self.comm_rank, self.comm_world = 0, 1
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -128,16 +129,26 @@ class ScoringEngine:
         """Bracket every scan launch with CUDA events; totals appear in ``info()['scan_ms']``."""
         self._check(self._lib.bb_set_profiling(self._h, 1 if enable else 0))
 
-    def export_threshold_handle(self) -> bytes:
-        """cudaIpc handle of this shard's per-query threshold array (row-sharded catalogs, see ShardedSearch)."""
+    def comm_export(self) -> bytes:
+        """cudaIpc handle of this shard's communication block (row-sharded catalogs, see ShardedSearch)."""
         buf = C.create_string_buffer(L.BB_IPC_HANDLE_BYTES)
-        self._check(self._lib.bb_export_threshold_handle(self._h, buf))
+        self._check(self._lib.bb_comm_export(self._h, buf))
         return buf.raw
 
-    def import_peer_thresholds(self, handles: Sequence[bytes]):
-        """Maps the threshold arrays of the OTHER ranks; the scan then raises them through NVLink peer memory."""
-        blob = b"".join(handles)
-        self._check(self._lib.bb_import_peer_thresholds(self._h, len(handles), C.c_char_p(blob) if handles else None))
+    def comm_import(self, rank: int, handles: Sequence[bytes]):
+        """Maps the communication blocks of all ranks (``handles[rank]`` is this rank's own and is ignored): the scan
+        then prunes against the union of all shards' thresholds and the merge kernel delivers candidates to the
+        queries' owner ranks through NVLink peer memory."""
+        blob = b"".join(h if h is not None else b"\0" * L.BB_IPC_HANDLE_BYTES for h in handles)
+        self._check(self._lib.bb_comm_import(self._h, rank, len(handles), C.c_char_p(blob)))
+        self.comm_rank, self.comm_world = rank, len(handles)
+
+    def comm_link_local(self, rank: int, engines: Sequence["ScoringEngine"]):
+        """Same as ``comm_import`` for shards that live in THIS process (several GPUs driven by one process, or several
+        shards on one GPU in tests)."""
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        self._check(self._lib.bb_comm_link_local(self._h, rank, len(engines), arr))
+        self.comm_rank, self.comm_world = rank, len(engines)
 
     @property
     def launches(self) -> int:
@@ -204,7 +215,7 @@ class ScoringEngine:
 
     # ------------------------------------------------------------------ the hot path
     def _batch(self, a: _Args, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2,
-               constraint_index=None):
+               constraint_index=None, allow_bitmaps=None, excl_lists=None, prenormalized=False):
         ref = next(x for x in (q_emb, q_item, q_cf) if x is not None)
         b = int(ref.shape[0])
         qb = L.bb_query_batch()
@@ -242,7 +253,20 @@ class ScoringEngine:
         qb.constraint_index = a.ptr(constraint_index, np.int32, (b,))
         qb.self_id = a.ptr(self_id, np.int32, (b,))
         qb.precision = L.PRECISIONS[precision]
-        qb.flags = L.BB_Q_SCORES_AS_L2 if as_l2 else 0
+        qb.flags = (L.BB_Q_SCORES_AS_L2 if as_l2 else 0) | (L.BB_Q_EMB_PRENORMALIZED if prenormalized else 0)
+        if allow_bitmaps is not None:
+            # per-CALL validity bitmaps [n, ceil(n_items/32)] (uint32 NumPy, or int32 / CUDA tensor as written by
+            # apply_constraints(device_out=True)); bb_constraint.allow_bitmap indexes this array for this call
+            words = (self.n_items + 31) // 32
+            n_allow = int(allow_bitmaps.shape[0]) if allow_bitmaps.ndim == 2 else 1
+            qb.allow_bitmaps = a.ptr(allow_bitmaps.reshape(n_allow, words), np.uint32, (n_allow, words))
+            qb.n_allow = n_allow
+        if excl_lists is not None:
+            # per-QUERY exclusion-list indices [B] or [B, n<=3] (-1 = none): the user's already-rated items
+            e = excl_lists if _is_torch(excl_lists) else np.asarray(excl_lists, dtype=np.int32)
+            e = e.reshape(b, -1)
+            qb.n_excl_per_query = int(e.shape[1])
+            qb.excl_lists = a.ptr(e, np.int32, (b, int(e.shape[1])))
         return qb, b
 
     @staticmethod
@@ -255,28 +279,67 @@ class ScoringEngine:
 
     def search(self, k: int, q_emb=None, q_item=None, q_cf=None, w_content=1.0, w_cf=0.0, constraints=None,
                self_id=None, precision: str = "fp32", as_l2: bool = False, out=None, stream=None,
-               constraint_index=None, share_thresholds: bool = False) -> Tuple[object, object]:
+               constraint_index=None, share_thresholds: bool = False, allow_bitmaps=None, excl_lists=None,
+               prenormalized: bool = False, sharded: bool = False) -> Tuple[object, object]:
         """Fused score + blend + mask + top-k.  Returns (scores[B,k] float32, ids[B,k] int32).
         Outputs are CUDA tensors when any input is a CUDA tensor (or ``out`` is given), else NumPy.
-        ``share_thresholds`` marks a collective search of a row-sharded catalog (``ShardedSearch``)."""
+        ``allow_bitmaps`` / ``excl_lists``: this call's validity bitmaps and the queries' own exclusion lists.
+        ``share_thresholds`` marks a collective search of a row-sharded catalog whose candidates the caller exchanges
+        (NCCL path of ``ShardedSearch``); ``sharded=True`` runs the whole collective inside the library
+        (``bb_search_sharded``) and returns the results of THIS rank's slice of the queries, [n_mine, k]."""
         a = _Args()
         qb, b = self._batch(a, q_emb, q_item, q_cf, w_content, w_cf, constraints, self_id, precision, as_l2,
-                            constraint_index)
+                            constraint_index, allow_bitmaps, excl_lists, prenormalized)
         if share_thresholds:
             qb.flags |= L.BB_Q_SHARE_THRESHOLDS
+        rows = b
+        if sharded and getattr(self, "comm_world", 1) > 1:
+            sl = -(-b // self.comm_world)
+            rows = max(0, min(sl, b - self.comm_rank * sl))
+        alloc = max(rows, 1)     # (an empty slice still takes part in the collective; the library needs valid pointers)
         if out is not None:
             scores, ids = out
-            ps, pi = a.ptr(scores, np.float32, (b, k)), a.ptr(ids, np.int32, (b, k))
+            ps, pi = a.ptr(scores, np.float32, (rows, k)), a.ptr(ids, np.int32, (rows, k))
         elif a.any_cuda:
-            scores = torch.empty((b, k), dtype=torch.float32, device=f"cuda:{self.device}")
-            ids = torch.empty((b, k), dtype=torch.int32, device=f"cuda:{self.device}")
-            ps, pi = scores.data_ptr(), ids.data_ptr()
+            fs = torch.empty((alloc, k), dtype=torch.float32, device=f"cuda:{self.device}")
+            fi = torch.empty((alloc, k), dtype=torch.int32, device=f"cuda:{self.device}")
+            ps, pi = fs.data_ptr(), fi.data_ptr()
+            scores, ids = fs[:rows], fi[:rows]
         else:
-            scores = np.empty((b, k), dtype=np.float32)
-            ids = np.empty((b, k), dtype=np.int32)
-            ps, pi = scores.ctypes.data, ids.ctypes.data
-        self._check(self._lib.bb_search(self._h, C.byref(qb), k, ps, pi, self._stream(stream)))
+            fs = np.empty((alloc, k), dtype=np.float32)
+            fi = np.empty((alloc, k), dtype=np.int32)
+            ps, pi = fs.ctypes.data, fi.ctypes.data
+            scores, ids = fs[:rows], fi[:rows]
+        fn = self._lib.bb_search_sharded if sharded else self._lib.bb_search
+        self._check(fn(self._h, C.byref(qb), k, ps, pi, self._stream(stream)))
         return scores, ids
+
+    def sharded_scatter(self, k: int, stream=None, **kwargs) -> int:
+        """First half of a collective search (``bb_sharded_scatter``): same query arguments as ``search``.  Returns the
+        number of query rows this rank owns.  For one thread that drives several shards: scatter on every shard,
+        then ``sharded_collect`` on every shard."""
+        a = _Args()
+        qb, b = self._batch(a, kwargs.get("q_emb"), kwargs.get("q_item"), kwargs.get("q_cf"), kwargs.get("w_content", 1.0),
+                            kwargs.get("w_cf", 0.0), kwargs.get("constraints"), kwargs.get("self_id"),
+                            kwargs.get("precision", "fp32"), kwargs.get("as_l2", False), kwargs.get("constraint_index"),
+                            kwargs.get("allow_bitmaps"), kwargs.get("excl_lists"), kwargs.get("prenormalized", False))
+        self._check(self._lib.bb_sharded_scatter(self._h, C.byref(qb), k, self._stream(stream)))
+        sl = -(-b // self.comm_world)
+        return max(0, min(sl, b - self.comm_rank * sl))
+
+    def sharded_collect(self, k: int, n_mine: int, device: bool = False, stream=None):
+        """Second half: (scores, ids) [n_mine, k] of this rank's slice of the queries."""
+        alloc = max(n_mine, 1)
+        if device:
+            fs = torch.empty((alloc, k), dtype=torch.float32, device=f"cuda:{self.device}")
+            fi = torch.empty((alloc, k), dtype=torch.int32, device=f"cuda:{self.device}")
+            ps, pi = fs.data_ptr(), fi.data_ptr()
+        else:
+            fs = np.empty((alloc, k), dtype=np.float32)
+            fi = np.empty((alloc, k), dtype=np.int32)
+            ps, pi = fs.ctypes.data, fi.ctypes.data
+        self._check(self._lib.bb_sharded_collect(self._h, ps, pi, self._stream(stream)))
+        return fs[:n_mine], fi[:n_mine]
 
     def debug_scores(self, q_emb=None, q_item=None, q_cf=None, w_content=1.0, w_cf=0.0,
                      precision: str = "fp32") -> np.ndarray:
@@ -354,13 +417,20 @@ class ScoringEngine:
                                               x.data_ptr(), l, out.data_ptr(), self._stream(stream)))
         return out
 
-    def item_item_topk(self, indptr, indices, values, n_items: int, k: int):
-        """Item-item cosine top-k from a user x item CSR rating matrix (BASELINE config 3)."""
+    def item_item_topk(self, indptr, indices, values, n_items: int, k: int, device_out: bool = False):
+        """Item-item cosine top-k from a user x item CSR rating matrix (BASELINE config 3).  The CSR arrays may be
+        NumPy or CUDA tensors; ``device_out`` leaves the lists on the device."""
         a = _Args()
         n_users = int(indptr.shape[0]) - 1
-        out_s = np.empty((n_items, k), dtype=np.float32)
-        out_i = np.empty((n_items, k), dtype=np.int32)
+        if device_out:
+            out_s = torch.empty((n_items, k), dtype=torch.float32, device=f"cuda:{self.device}")
+            out_i = torch.empty((n_items, k), dtype=torch.int32, device=f"cuda:{self.device}")
+            ps, pi = out_s.data_ptr(), out_i.data_ptr()
+        else:
+            out_s = np.empty((n_items, k), dtype=np.float32)
+            out_i = np.empty((n_items, k), dtype=np.int32)
+            ps, pi = out_s.ctypes.data, out_i.ctypes.data
         self._check(self._lib.bb_item_item_topk(self._h, n_users, n_items, a.ptr(indptr, np.int64),
                                                 a.ptr(indices, np.int32), a.ptr(values, np.float32), k,
-                                                out_s.ctypes.data, out_i.ctypes.data, self._stream(None)))
+                                                ps, pi, self._stream(None)))
         return out_s, out_i

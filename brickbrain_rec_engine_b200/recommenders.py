@@ -110,11 +110,29 @@ class CatalogTable:
                                     num_parts=int(self.num_parts[idx]), img_url=self.img_urls[idx])
 
 
-def _filter_bitmap(catalog: CatalogTable, valid_set_filter) -> Optional[np.ndarray]:
-    """``valid_set_filter`` (list of set_nums, or an already packed uint32 bitmap) -> packed bitmap.
+class DeviceFilter:
+    """A ``valid_set_filter`` that already lives on the GPU: the validity bitmap written by the mask kernel
+    (``HardConstraintFilter.apply_constraints``).  ``HybridRecommender.get_recommendations`` hands it to both
+    recommenders, so the request's filter never makes the round trip bitmap -> list of set_nums -> bitmap."""
+
+    def __init__(self, bitmap, count: int):
+        self.bitmap = bitmap            # CUDA tensor int32 [1, words] (or uint32 NumPy on CPU test doubles)
+        self.count = int(count)
+
+    def __len__(self):
+        return self.count
+
+    def __bool__(self):
+        return self.count > 0
+
+
+def _filter_bitmap(catalog: CatalogTable, valid_set_filter):
+    """``valid_set_filter`` (list of set_nums, an already packed uint32 bitmap, or a ``DeviceFilter``) -> packed bitmap.
     A falsy filter means "no filter", as in the reference (``if valid_set_filter and ...``, :229, :454)."""
     if valid_set_filter is None:
         return None
+    if isinstance(valid_set_filter, DeviceFilter):
+        return valid_set_filter.bitmap if valid_set_filter else None
     if isinstance(valid_set_filter, np.ndarray) and valid_set_filter.dtype == np.uint32:
         return valid_set_filter
     if len(valid_set_filter) == 0:
@@ -122,6 +140,15 @@ def _filter_bitmap(catalog: CatalogTable, valid_set_filter) -> Optional[np.ndarr
     mask = np.zeros(len(catalog), dtype=bool)
     mask[[catalog.index_of[s] for s in valid_set_filter if s in catalog.index_of]] = True
     return ScoringEngine.pack_bitmap(mask)
+
+
+def _clamp_k(top_k: int, engine) -> int:
+    """The engine selects at most ``k_max`` (<= 128) results per query; the reference has no such limit (its API caps
+    top_k at 50, recommendation_api.py:243, i.e. 100 for the hybrid's top_k * 2).  Larger requests are truncated loudly."""
+    if top_k > engine.k_max:
+        logger.warning("top_k=%d exceeds the engine's k_max=%d: returning the best %d", top_k, engine.k_max, engine.k_max)
+        return engine.k_max
+    return top_k
 
 
 class ContentBasedRecommender:
@@ -155,13 +182,15 @@ class ContentBasedRecommender:
         """Batched: rows of the catalog as queries; self excluded (== the reference's rank-0 drop whenever
         the target is its own best match, :217)."""
         rows = np.asarray(target_rows, dtype=np.int32) + np.int32(self.engine.id_offset)
-        cons = None
-        if bitmap is not None:
-            self.engine.set_allow_bitmaps(bitmap.reshape(1, -1))
+        cons = allow = None
+        if bitmap is not None:                      # the request's filter travels WITH the call (no handle state)
+            allow = bitmap.reshape(1, -1)
             cons = L.no_constraint()
             cons["allow_bitmap"] = 0
-        scores, ids = self.engine.search(min(top_k, self.engine.k_max), q_item=rows, self_id=rows, w_content=1.0,
-                                         w_cf=0.0, constraints=cons, precision=self.precision)
+        scores, ids = self.engine.search(_clamp_k(top_k, self.engine), q_item=rows, self_id=rows, w_content=1.0,
+                                         w_cf=0.0, constraints=cons, allow_bitmaps=allow, precision=self.precision)
+        if hasattr(scores, "cpu"):                  # (a device-resident filter makes the outputs CUDA tensors)
+            scores, ids = scores.cpu().numpy(), ids.cpu().numpy()
         return ids, scores
 
     def _hydrate(self, target: int, ids: np.ndarray, scores: np.ndarray) -> List[RecommendationResult]:
@@ -228,9 +257,48 @@ class CollaborativeFilteringRecommender:
             logger.warning("Not enough components for SVD, using fallback recommendations")
             self.svd_model = None
             return
+        frame = getattr(self, "user_item_matrix", None)
         self.user_factors, self.item_factors, _ = truncated_svd(self.engine, m, n_components)
+        self.user_factors = np.ascontiguousarray(self.user_factors, dtype=np.float32)
+        self._adopt_trained_factors(frame, m)
         self.svd_model = object()
         logger.info(f"Trained SVD model with {n_components} components")
+
+    def _adopt_trained_factors(self, frame, m):
+        """The reference's ``train_svd_model`` leaves the recommender ready to score (:402-407 + the lookups of
+        :332-337).  Here that means: the new item factors go into the engine's operand (factor-only reload), the user
+        lookup follows the matrix index, and the already-rated lists / the CF universe are rebuilt from the matrix."""
+        eng = self.engine
+        f = int(self.item_factors.shape[1])
+        if eng.cf_dim < f:
+            raise ValueError(f"engine was created with cf_dim={eng.cf_dim} but the trained model has {f} components: "
+                             "create the engine with cf_dim >= n_components (HybridRecommender.from_arrays(cf_dim=...))")
+        n = len(self.catalog)
+        # columns of the matrix -> catalog rows (a pivot table names them by set_num, a plain array is positional)
+        if hasattr(frame, "columns") and hasattr(frame, "index"):
+            cols = np.array([self.catalog.index_of.get(c, -1) for c in frame.columns], dtype=np.int64)
+            users = list(frame.index)
+        else:
+            cols = np.arange(m.shape[1], dtype=np.int64)
+            users = list(self.user_lookup) if len(self.user_lookup) == m.shape[0] else list(range(m.shape[0]))
+        keep = cols >= 0
+        full = np.zeros((n, eng.cf_dim), dtype=np.float32)
+        full[cols[keep], :f] = np.asarray(self.item_factors, dtype=np.float32)[keep]
+        eng.load_catalog(item_factors=full)                       # factor-only reload: embeddings and metadata are kept
+        if eng.cf_dim > f:
+            self.user_factors = np.ascontiguousarray(np.pad(self.user_factors, ((0, 0), (0, eng.cf_dim - f))))
+        self.user_lookup = {u: i for i, u in enumerate(users)}
+        self.cf_universe = np.zeros(n, dtype=bool)
+        self.cf_universe[cols[keep]] = True
+        dense = m.toarray() if hasattr(m, "toarray") else np.asarray(m)
+        self.rated = {u: np.sort(cols[keep][np.nonzero(dense[i][keep] > 0)[0]]).astype(np.int32) for i, u in enumerate(users)}
+        # the engine's exclusion lists are shared with the constraint filter (owned / wishlisted): append / replace the
+        # rated lists through its owner when there is one
+        if getattr(self, "constraint_filter", None) is not None:
+            self.rated_list_index = self.constraint_filter.replace_rated_lists(self.rated)
+        else:
+            eng.set_exclusion_lists([self.rated[u] for u in users])
+            self.rated_list_index = {u: i for i, u in enumerate(users)}
 
     def get_recommendations(self, user_id, top_k: int = 10,
                             valid_set_filter: Optional[List[str]] = None) -> List[RecommendationResult]:
@@ -253,19 +321,25 @@ class CollaborativeFilteringRecommender:
         if self.cf_universe is not None:
             allow = ScoringEngine.pack_bitmap(self.cf_universe)
         if bitmap is not None:
-            allow = bitmap if allow is None else (allow & bitmap)
-        cons = np.stack([L.no_constraint() for _ in user_ids])
-        if allow is not None:
-            self.engine.set_allow_bitmaps(allow.reshape(1, -1))
+            if allow is None:
+                allow = bitmap
+            elif hasattr(bitmap, "is_cuda"):        # device-resident request filter AND the CF universe
+                import torch
+                u = torch.from_numpy(allow.view(np.int32)).to(bitmap.device)
+                allow = torch.bitwise_and(bitmap.reshape(-1), u)
+            else:
+                allow = allow & bitmap
+        cons = None
+        if allow is not None:                       # the request's filter travels WITH the call (no handle state)
+            cons = L.no_constraint()
             cons["allow_bitmap"] = 0
-        for j, u in enumerate(user_ids):
-            li = self.rated_list_index.get(u)
-            if li is not None:
-                ex = cons["excl_list"][j]
-                ex[0] = li
-                cons["excl_list"][j] = ex
-        scores, ids = self.engine.search(min(top_k, self.engine.k_max), q_cf=q, w_content=0.0, w_cf=1.0,
-                                         constraints=cons, precision=self.precision)
+            allow = allow.reshape(1, -1)
+        # the users' already-rated items (:441-451) are per-QUERY exclusion lists, not part of a constraint set
+        excl = np.array([[self.rated_list_index.get(u, -1)] for u in user_ids], dtype=np.int32)
+        scores, ids = self.engine.search(_clamp_k(top_k, self.engine), q_cf=q, w_content=0.0, w_cf=1.0,
+                                         constraints=cons, allow_bitmaps=allow, excl_lists=excl, precision=self.precision)
+        if hasattr(scores, "cpu"):
+            scores, ids = scores.cpu().numpy(), ids.cpu().numpy()
         del n
         return ids, scores
 
@@ -326,11 +400,19 @@ class HybridRecommender:
                     owned: Optional[Dict[Any, Sequence[int]]] = None,
                     wishlisted: Optional[Dict[Any, Sequence[int]]] = None, cf_universe: Optional[np.ndarray] = None,
                     ratings_summary: Optional[dict] = None, device: int = 0, precision: str = "fp32",
-                    k_max: int = 128) -> "HybridRecommender":
+                    k_max: int = 128, cf_dim: Optional[int] = None) -> "HybridRecommender":
+        """``cf_dim``: factor width of the engine when no ``item_factors`` are given yet (``train_svd_model`` later
+        loads them; the reference trains up to 50 components, recommendation_system.py:368)."""
+        from .constraints import theme_bits_for
         n = len(catalog)
         feat = np.ascontiguousarray(feat_matrix, dtype=np.float32)
-        f = 0 if item_factors is None else int(item_factors.shape[1])
-        eng = ScoringEngine(n_items=n, dim=int(feat.shape[1]), cf_dim=f, device=device, k_max=k_max)
+        f = (cf_dim or 0) if item_factors is None else int(item_factors.shape[1])
+        if catalog.theme_id.max(initial=-1) > 32767 or catalog.year.max(initial=0) > 32767 or catalog.year.min(initial=0) < -32768:
+            raise ValueError("theme_id / year do not fit the engine's int16 metadata columns")
+        eng = ScoringEngine(n_items=n, dim=int(feat.shape[1]), cf_dim=f, device=device, k_max=k_max,
+                            theme_bits=theme_bits_for(themes, catalog.theme_id))
+        if item_factors is None and f > 0:
+            item_factors = np.zeros((n, f), dtype=np.float32)
         theme16 = np.where(catalog.theme_id < 0, -1, catalog.theme_id).astype(np.int16)
         eng.load_catalog(emb=feat, item_factors=None if item_factors is None else np.asarray(item_factors, np.float32),
                          num_parts=np.clip(catalog.num_parts, -2**31, 2**31 - 1).astype(np.int32),
@@ -342,6 +424,7 @@ class HybridRecommender:
         cf = CollaborativeFilteringRecommender(engine=eng, catalog=catalog, user_ids=user_ids, user_factors=user_factors,
                                                rated=rated, rated_list_index=rated_idx, cf_universe=cf_universe,
                                                ratings_summary=ratings_summary, precision=precision)
+        cf.constraint_filter = filt            # owner of the engine's exclusion lists (re-training replaces the rated ones)
         return cls(engine=eng, content=content, collaborative=cf, constraint_filter=filt)
 
     # ------------------------------------------------------------------ reference surface
@@ -359,12 +442,16 @@ class HybridRecommender:
                 return [], constraint_result
         content_recs: List[RecommendationResult] = []
         collaborative_recs: List[RecommendationResult] = []
+        # the validity bitmap the mask kernel just wrote stays on the device for both searches
+        valid_filter = valid_set_nums
+        if constraint_result is not None and getattr(constraint_result, "device_bitmap", None) is not None:
+            valid_filter = DeviceFilter(constraint_result.device_bitmap, len(valid_set_nums))
         if liked_set:
             content_recs = self.content_recommender.get_similar_sets(liked_set, top_k * 2,
-                                                                    valid_set_filter=valid_set_nums)
+                                                                    valid_set_filter=valid_filter)
         if user_id:
             collaborative_recs = self.collaborative_recommender.get_recommendations(user_id, top_k * 2,
-                                                                                   valid_set_filter=valid_set_nums)
+                                                                                   valid_set_filter=valid_filter)
         if not content_recs and collaborative_recs:
             final_recs = collaborative_recs[:top_k]
         elif content_recs and not collaborative_recs:
@@ -476,23 +563,18 @@ class HybridRecommender:
         descs = []
         for j in range(b):
             cons_j = constraints[j] if constraints is not None else None
-            rated_user = user_ids[j] if (exclude_rated and user_ids is not None) else None
-            if cons_j is not None:
-                d = self.constraint_filter.descriptor(cons_j, rated_user=rated_user)
-            else:
-                d = L.no_constraint()
-                li = cf.rated_list_index.get(rated_user) if rated_user is not None else None
-                if li is not None:
-                    ex = d["excl_list"]
-                    ex[0] = li
-                    d["excl_list"] = ex
-            descs.append(d)
+            descs.append(self.constraint_filter.descriptor(cons_j) if cons_j is not None else L.no_constraint())
+        # the users' already-rated items are per-QUERY exclusion lists: they do not make the constraint sets distinct
+        excl = None
+        if exclude_rated and user_ids is not None:
+            excl = np.array([[cf.rated_list_index.get(u, -1)] for u in user_ids], dtype=np.int32)
         # queries that share a constraint set (popular filters) share one validity bitmap on the device
         distinct, index = ScoringEngine.dedupe_constraints(np.stack(descs))
         return self.engine.search(top_k, q_item=q_item, q_cf=q_cf,
                                   w_content=self.content_weight if q_item is not None else 0.0,
                                   w_cf=self.collaborative_weight if q_cf is not None else 0.0,
-                                  constraints=distinct, constraint_index=index, self_id=self_id, precision=precision)
+                                  constraints=distinct, constraint_index=index, self_id=self_id, excl_lists=excl,
+                                  precision=precision)
 
 
 def accelerate(reference_hybrid, themes: Dict[int, str], owned=None, wishlisted=None, device: int = 0,

@@ -161,3 +161,66 @@ def make_query_vector_database(store: BrickVectorStore) -> Callable[[np.ndarray,
             return []
 
     return _query_vector_database
+
+
+# ---------------------------------------------------------------------------------------------
+# the callers' post-filters (what happens to the store's hits before they are returned)
+# ---------------------------------------------------------------------------------------------
+def _document_rules(filters: Dict[str, Any]):
+    """The legacy recommender's post-filter (lego_nlp_recommeder.py:1514-1549) as a list of predicates over a document's
+    metadata; a falsy filter value means "not set", as in the reference."""
+    f = filters or {}
+    rules = []
+    if f.get("min_pieces"):
+        rules.append(lambda m, v=f["min_pieces"]: m["num_parts"] >= v)
+    if f.get("max_pieces"):
+        rules.append(lambda m, v=f["max_pieces"]: m["num_parts"] <= v)
+    if f.get("themes"):
+        wanted = [t.lower() for t in f["themes"]]
+        rules.append(lambda m: any(t in m["theme"].lower() for t in wanted))          # substring, case-insensitive
+    if f.get("complexity"):
+        rules.append(lambda m, v=f["complexity"]: m.get("complexity") == v)
+    if f.get("min_age"):
+        rules.append(lambda m: m["year"] >= 2010)                                     # "newer sets for younger builders"
+    return rules
+
+
+def apply_document_filters(docs: Sequence[Document], filters: Optional[Dict[str, Any]]) -> List[Document]:
+    """``NLPRecommender._apply_filters``: keeps the documents whose metadata passes every active rule, in order."""
+    rules = _document_rules(filters)
+    return [d for d in docs if all(rule(d.metadata) for rule in rules)]
+
+
+_RESULT_RULES = (          # (filter key, result key, keep-if) of hf_nlp_recommender.py:1351-1386
+    ("themes", "theme", lambda have, want: have in want),
+    ("min_pieces", "num_parts", lambda have, want: have >= want),
+    ("max_pieces", "num_parts", lambda have, want: have <= want),
+    ("min_age", "min_age", lambda have, want: have <= want),
+    ("max_age", "max_age", lambda have, want: have >= want),
+)
+
+
+def apply_result_filters(results: Sequence[Dict], filters: Optional[Dict[str, Any]]) -> List[Dict]:
+    """``HuggingFaceNLPRecommender._apply_filters``: a rule only applies when BOTH the filter value and the result's
+    field are truthy (a hit without ``min_age`` passes the age filter); themes match by exact membership."""
+    if not filters:
+        return list(results)
+    active = [(rk, keep, filters[fk]) for fk, rk, keep in _RESULT_RULES if filters.get(fk)]
+    return [r for r in results if all(not r.get(rk) or keep(r[rk], want) for rk, keep, want in active)]
+
+
+def semantic_search(store: BrickVectorStore, query, top_k: int = 10, filters: Optional[Dict[str, Any]] = None,
+                    retrieve_k: int = 20) -> List[Dict]:
+    """The search half of ``NLPRecommender.semantic_search`` (lego_nlp_recommeder.py:1394-1411): the retriever's best
+    ``retrieve_k`` documents (k=20, :305) -> post-filter -> ``[:top_k]``.  Like the reference, nothing is re-fetched
+    when the filter removes hits, so fewer than ``top_k`` results may come back.  ``query``: text (needs the store's
+    embedding function) or an embedding vector."""
+    if isinstance(query, str):
+        hits = store.similarity_search_with_score(query, k=retrieve_k)
+    else:
+        hits = store.similarity_search_with_score_by_vector(query, k=retrieve_k)
+    kept = apply_document_filters([d for d, _ in hits], filters)
+    score_of = {id(d): s for d, s in hits}
+    return [{"set_num": d.metadata["set_num"], "name": d.metadata["name"], "year": d.metadata["year"],
+             "num_parts": d.metadata["num_parts"], "theme": d.metadata["theme"], "description": d.page_content,
+             "score": score_of[id(d)]} for d in kept[:top_k]]

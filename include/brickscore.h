@@ -59,7 +59,8 @@ extern "C" {
 
 /* bb_query_batch.flags */
 #define BB_Q_SCORES_AS_L2 1u /* report 2 - 2*score (FAISS IndexFlatL2 distance on unit vectors) */
-#define BB_Q_SHARE_THRESHOLDS 2u /* collective search of a row-sharded catalog, see bb_import_peer_thresholds */
+#define BB_Q_SHARE_THRESHOLDS 2u /* collective search of a row-sharded catalog (union thresholds over peer memory), see bb_comm_import */
+#define BB_Q_EMB_PRENORMALIZED 4u /* q_emb rows are stored catalog rows (already unit norm): use them as they are */
 
 /* bb_constraint.flags */
 #define BB_C_ALWAYS_FALSE 1u /* THEMES_REQUIRED matched no theme: "1=0" (hard_constraint_filter.py:408-409) */
@@ -114,6 +115,17 @@ typedef struct bb_query_batch {
   const int32_t* self_id;           /* [B] global id excluded per query (-1 none), or NULL */
   int32_t precision;                /* BB_PREC_* */
   uint32_t flags;                   /* BB_Q_* */
+  /* Per-CALL validity bitmaps over LOCAL rows, [n_allow x ceil(n_items/32)] words, host or device memory: the
+   * valid_set_filter of ONE request (recommendation_system.py:229,454), e.g. the device bitmap written by
+   * bb_apply_constraints.  When given, bb_constraint.allow_bitmap indexes THIS array instead of the handle-resident
+   * one (bb_set_allow_bitmaps), so concurrent requests never share filter state.  NULL = handle-resident bitmaps. */
+  const uint32_t* allow_bitmaps;
+  int32_t n_allow;
+  /* Per-QUERY exclusion lists: [B x n_excl_per_query] indices into bb_set_exclusion_lists (-1 = none): the user's
+   * already-rated items (recommendation_system.py:441-451).  Kept out of bb_constraint so that queries that share a
+   * constraint set still share one descriptor (and one validity bitmap) while every user carries an own list. */
+  int32_t n_excl_per_query;         /* 0..3 */
+  const int32_t* excl_lists;
 } bb_query_batch;
 
 typedef struct bb_info {
@@ -228,19 +240,35 @@ BB_API int bb_item_item_topk(bb_handle* h, int64_t n_users, int32_t n_items, con
                       const float* values, int32_t k, float* out_scores, int32_t* out_ids, void* stream);
 
 /*
- * Row-sharded catalogs (one process per GPU): the per-query running thresholds of the scan can be shared between
- * the ranks through NVLink peer memory, so that every shard prunes with the best bound any shard has found (a
- * rank's local k-th best is a valid lower bound of the global k-th best).  Each rank exports the handle of its
- * threshold array (requires bb_config.max_batch > 0), the ranks exchange the 64-byte handles (e.g. all-gather) and
- * import the other ranks' handles (a collective: every rank imports before any rank searches again).  Searches
- * flagged BB_Q_SHARE_THRESHOLDS are then collective too: all ranks issue the same sequence of them with the same
- * replicated query batch, one at a time.  The merged result is unchanged; a rank's own output may hold fewer than
- * k entries (-1 padded), since items that cannot reach the global top-k are pruned early.  Unflagged searches are
- * unaffected.
+ * Row-sharded catalogs: every rank (one process per GPU, or several handles in one process) holds a
+ * contiguous range of rows; queries are replicated.  Each handle created with max_batch > 0 owns a COMMUNICATION
+ * BLOCK of device memory that the other ranks map (cudaIpc across processes, peer access inside one):
+ *   - threshold + level words: while scanning, every rank publishes per query "I hold >= k'/8, k'/4, k'/2, k'
+ *     candidates with score >= T"; if `need` ranks each hold m candidates >= T and need * m >= k', T is a lower bound
+ *     of the GLOBAL k'-th best.  A poller warp of the scan kernel reads the peers' words over NVLink (plain loads) and
+ *     raises the local threshold, so every shard prunes against the global running top-k' instead of its own;
+ *   - an inbox + arrival counters: query q is owned by rank q / ceil(B / world); the merge kernel of every rank
+ *     stores its k final (score, id) keys of q straight into the owner's inbox (peer stores fused into the kernel)
+ *     and the owner merges the `world` lists of its slice.
+ * Setup is collective: every rank exports its handle, the handles are exchanged (e.g. all-gather) and imported, in
+ * rank order, before any rank searches.  bb_search_sharded is collective too: all ranks issue the same sequence of
+ * sharded searches with the same replicated batch.  Its outputs are the results of THIS rank's slice of the queries,
+ * rows [rank * slice, min(B, (rank + 1) * slice)), slice = ceil(B / world): out_* are [n_mine x k].
+ * bb_search with BB_Q_SHARE_THRESHOLDS only shares the thresholds and leaves the shard-local candidates in out_*
+ * (fewer than k entries, -1 padded, where the global bound pruned the rest) for an external exchange (NCCL all-gather
+ * + bb_merge_topk).
  */
 #define BB_IPC_HANDLE_BYTES 64
-BB_API int bb_export_threshold_handle(bb_handle* h, void* out_handle);
-BB_API int bb_import_peer_thresholds(bb_handle* h, int32_t n_peers, const void* handles);
+BB_API int bb_comm_export(bb_handle* h, void* out_handle);
+BB_API int bb_comm_import(bb_handle* h, int32_t rank, int32_t world, const void* handles /* world x 64 B, own entry ignored */);
+/* same process (several GPUs, or several shards on one GPU in tests): handles[world], own entry ignored */
+BB_API int bb_comm_link_local(bb_handle* h, int32_t rank, int32_t world, bb_handle* const* handles);
+BB_API int bb_search_sharded(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_scores, int32_t* out_ids, void* stream);
+/* The two halves of bb_search_sharded, for callers that drive several shards from ONE thread (a process with several
+ * GPUs, or several shards on one GPU): scatter on every shard first, then collect on every shard.  scatter only
+ * enqueues work; collect waits on the device until all ranks' keys of this rank's slice have arrived. */
+BB_API int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* stream);
+BB_API int bb_sharded_collect(bb_handle* h, float* out_scores, int32_t* out_ids, void* stream);
 
 /*
  * Sparse (CSR ratings, fp32 values) x dense (fp64, row-major) product, Y[n_rows x L] = A[n_rows x n_cols] * X[n_cols x L]:

@@ -479,23 +479,49 @@ def reference_style_query(q_emb: np.ndarray, q_cf: np.ndarray, emb: np.ndarray, 
 
 
 def batched_cpu_topk(q_cat: np.ndarray, e_cat: np.ndarray, k: int,
-                     valid: Optional[np.ndarray] = None, block: int = 65536) -> Tuple[np.ndarray, np.ndarray]:
+                     valid: Optional[np.ndarray] = None, block: int = 65536,
+                     class_valid: Optional[np.ndarray] = None, class_index: Optional[np.ndarray] = None,
+                     exclusions: Optional[np.ndarray] = None, self_ids: Optional[np.ndarray] = None
+                     ) -> Tuple[np.ndarray, np.ndarray]:
     """Best-effort CPU restatement used as ``cpu_baseline`` (kind "port"):
     blocked fp32 sgemm (all BLAS threads) over the concatenated operands
-    [w_c*q_hat | w_f*u] x [e_hat | v], optional [N] validity mask, and a running
-    top-k: the first block is partitioned, later blocks only keep scores above each
-    row's current k-th best (vectorized compare + one sort of the survivors), so the
-    selection cost stays well below the sgemm.  BASELINE.md section 4 item 2."""
+    [w_c*q_hat | w_f*u] x [e_hat | v], validity mask, and a running top-k: the first
+    block is partitioned, later blocks only keep scores above each row's current k-th
+    best (vectorized compare + one sort of the survivors), so the selection cost stays
+    well below the sgemm.  BASELINE.md section 4 item 2.
+
+    Masks: ``valid`` [N] shared by all queries, or -- the GPU arm's workload --
+    ``class_valid`` [C, N] (one mask per distinct constraint set,
+    hard_constraint_filter.py:318-480) with ``class_index`` [B]; ``exclusions`` [B, R]
+    already-rated item ids per query (recommendation_system.py:441-451) and
+    ``self_ids`` [B] (the rank-0 drop of :217)."""
     b = q_cat.shape[0]
     n = e_cat.shape[0]
     best_s = np.full((b, k), -np.inf, dtype=np.float32)
     best_i = np.full((b, k), -1, dtype=np.int64)
-    penalty = None if valid is None else np.where(valid, np.float32(0), np.float32(-np.inf)).astype(np.float32)
+    ninf = np.float32(-np.inf)
+    penalty = None if valid is None else np.where(valid, np.float32(0), ninf).astype(np.float32)
+    class_pen = None
+    if class_valid is not None:
+        class_pen = np.where(class_valid, np.float32(0), ninf).astype(np.float32)
+        groups = [np.nonzero(class_index == c)[0] for c in range(class_valid.shape[0])]
+    rows_b = np.arange(b)
     for lo in range(0, n, block):
         hi = min(n, lo + block)
         s = q_cat @ e_cat[lo:hi].T
         if penalty is not None:
             s += penalty[None, lo:hi]
+        if class_pen is not None:
+            for c, g in enumerate(groups):
+                if g.size:
+                    s[g] += class_pen[c, lo:hi][None, :]
+        if exclusions is not None:
+            m = (exclusions >= lo) & (exclusions < hi)
+            rr = np.broadcast_to(rows_b[:, None], exclusions.shape)
+            s[rr[m], exclusions[m] - lo] = ninf
+        if self_ids is not None:
+            m = (self_ids >= lo) & (self_ids < hi)
+            s[rows_b[m], self_ids[m] - lo] = ninf
         if lo == 0:
             kk = min(k, hi - lo)
             part = np.argpartition(-s, kk - 1, axis=1)[:, :kk]
@@ -517,5 +543,67 @@ def batched_cpu_topk(q_cat: np.ndarray, e_cat: np.ndarray, k: int,
         keep = rank < k
         best_s = all_s[keep].reshape(b, k)
         best_i = all_i[keep].reshape(b, k)
+    best_i = np.where(np.isneginf(best_s), -1, best_i)
     order = np.lexsort((best_i, -best_s), axis=1)
     return np.take_along_axis(best_i, order, axis=1), np.take_along_axis(best_s, order, axis=1)
+
+
+# --------------------------------------------------------------------------------------
+# a11 / a12 -- post-filters of the semantic-search callers (results of the vector store -> what the caller returns)
+# --------------------------------------------------------------------------------------
+
+def nlp_post_filter(metadatas: Sequence[dict], filters: dict) -> List[int]:
+    """``NLPRecommender._apply_filters`` (lego_nlp_recommeder.py:1514-1549) over the metadata dicts of the retrieved
+    documents (built at :245-255), returning the indices that survive, in order.  Truthiness rules are the
+    reference's: a filter value of 0 / None / '' / [] is "not set"; ``min_age`` of any truthy value means
+    ``year >= 2010``; themes match by case-insensitive substring; complexity by equality."""
+    keep = []
+    for i, m in enumerate(metadatas):
+        if filters.get('min_pieces') and m['num_parts'] < filters['min_pieces']:
+            continue
+        if filters.get('max_pieces') and m['num_parts'] > filters['max_pieces']:
+            continue
+        if filters.get('themes'):
+            if not any(t.lower() in m['theme'].lower() for t in filters['themes']):
+                continue
+        if filters.get('complexity') and m.get('complexity') != filters['complexity']:
+            continue
+        if filters.get('min_age') and m['year'] < 2010:
+            continue
+        keep.append(i)
+    return keep
+
+
+def semantic_search_post(ranked_ids: Sequence[int], metadatas: Sequence[dict], filters: dict, top_k: int,
+                         retrieve_k: int = 20) -> List[int]:
+    """``semantic_search`` after the embedding step (lego_nlp_recommeder.py:1394-1401): the retriever returns the best
+    ``retrieve_k`` documents (k=20, :305), the post-filter runs on THOSE, then ``[:top_k]`` -- so fewer than top_k
+    results come back when the filter removes retrieved documents (nothing is re-fetched).  ``ranked_ids``: the exact
+    flat-search ranking of the catalog for the query; returns catalog indices."""
+    got = list(ranked_ids[:retrieve_k])
+    keep = nlp_post_filter([metadatas[i] for i in got], filters)
+    return [got[j] for j in keep][:top_k]
+
+
+def hf_post_filter(results: Sequence[dict], filters: dict) -> List[int]:
+    """``HuggingFaceNLPRecommender._apply_filters`` (hf_nlp_recommender.py:1351-1386) over result dicts; returns the
+    surviving indices (all of them when ``filters`` is falsy).  Exact theme-name membership; every predicate is skipped
+    when either side is falsy (a result without ``min_age`` passes the age filter)."""
+    if not filters:
+        return list(range(len(results)))
+    keep = []
+    for i, r in enumerate(results):
+        ok = True
+        if filters.get('themes') and r.get('theme') and r['theme'] not in filters['themes']:
+            ok = False
+        if filters.get('min_pieces') and r.get('num_parts') and r['num_parts'] < filters['min_pieces']:
+            ok = False
+        if filters.get('max_pieces') and r.get('num_parts') and r['num_parts'] > filters['max_pieces']:
+            ok = False
+        if filters.get('min_age') and r.get('min_age') and r['min_age'] > filters['min_age']:
+            ok = False
+        if filters.get('max_age') and r.get('max_age') and r['max_age'] < filters['max_age']:
+            ok = False
+        if ok:
+            keep.append(i)
+    return keep

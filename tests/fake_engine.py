@@ -59,6 +59,9 @@ class FakeEngine:
         if theme_id is not None:
             self.theme[sl] = theme_id
 
+    def fetch_embeddings(self, ids):
+        return self.emb[np.asarray(ids) - self.id_offset].copy()
+
     def set_exclusion_lists(self, lists):
         self.excl = [np.asarray(l) for l in lists]
 
@@ -77,8 +80,11 @@ class FakeEngine:
     dedupe_constraints = staticmethod(lambda c: __import__("brickbrain_rec_engine_b200").ScoringEngine.dedupe_constraints(c))
 
     def search(self, k, q_emb=None, q_item=None, q_cf=None, w_content=1.0, w_cf=0.0, constraints=None, self_id=None,
-               precision="fp32", as_l2=False, out=None, stream=None, constraint_index=None):
+               precision="fp32", as_l2=False, out=None, stream=None, constraint_index=None, share_thresholds=False,
+               allow_bitmaps=None, excl_lists=None, prenormalized=False, sharded=False):
         self.calls.append("search")
+        q_emb, q_cf, q_item, self_id, constraint_index, excl_lists = (
+            None if x is None else np.asarray(x) for x in (q_emb, q_cf, q_item, self_id, constraint_index, excl_lists))
         ref = next(x for x in (q_emb, q_item, q_cf) if x is not None)
         b = ref.shape[0]
         qe = None
@@ -94,8 +100,23 @@ class FakeEngine:
         if constraints is not None:
             c = np.atleast_1d(constraints)
             pick = (lambda j: int(constraint_index[j])) if constraint_index is not None else (lambda j: j if c.shape[0] > 1 else 0)
-            valid = np.stack([self._valid(c[pick(j)]) for j in range(b)])
-        sid = None if self_id is None else np.asarray(self_id) - self.id_offset
+            allow = self.allow if allow_bitmaps is None else list(np.asarray(allow_bitmaps, dtype=np.uint32).reshape(-1, (self.n_items + 31) // 32))
+            valid = np.stack([eval_descriptor(c[pick(j)], self.num_parts, self.year, self.theme, self.theme_sets, allow,
+                                              self.excl, self.id_offset) for j in range(b)])
+        if excl_lists is not None:                      # the queries' own exclusion lists (already-rated items)
+            if valid is None:
+                valid = np.ones((b, self.n_items), dtype=bool)
+            e = excl_lists.reshape(b, -1)
+            for j in range(b):
+                for l in e[j]:
+                    if l >= 0:
+                        ids_l = np.asarray(self.excl[int(l)]) - self.id_offset
+                        ids_l = ids_l[(ids_l >= 0) & (ids_l < self.n_items)]
+                        valid[j, ids_l] = False
+        sid = None
+        if self_id is not None:                         # a global id outside this shard excludes nothing here
+            sid = np.asarray(self_id, dtype=np.int64) - self.id_offset
+            sid = np.where((sid >= 0) & (sid < self.n_items), sid, -1)
         ids, sc = bo.fused_hybrid_topk(s, k, valid=valid, self_ids=sid)
         ids = np.where(ids >= 0, ids + self.id_offset, -1).astype(np.int32)
         sc = sc.astype(np.float32)

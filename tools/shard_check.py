@@ -3,10 +3,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/shard_check.py
 
-Every rank holds one shard; ``ShardedSearch`` (NCCL all-gather of the per-shard top-k + merge, running thresholds
-shared through NVLink peer memory) must return exactly what ONE engine over the whole catalog returns, with and
-without threshold sharing, on the exact fp32 path, and the same recall on the bf16 + re-score path.  Also prints
-how many candidates each shard's scan inserted with / without sharing (the point of sharing).
+Every rank holds one shard; ``ShardedSearch`` must return exactly what ONE engine over the whole catalog returns, on
+the exact fp32 path bit for bit and with recall >= 0.999 on the bf16 + re-score path, through BOTH exchanges: ``p2p``
+(union thresholds over NVLink peer memory + owner inboxes, fused into the kernels) and ``nccl`` (all-gather + merge
+kernel), with host and device inputs, for ``q_emb`` and for ``q_item`` queries (resolved by the owner shard).  Prints
+how many candidates each shard's scan appended with / without the union thresholds.
 """
 import os
 import sys
@@ -20,7 +21,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import synth  # noqa: E402
-from brickbrain_rec_engine_b200 import ScoringEngine, ShardedSearch, shard_bounds  # noqa: E402
+from brickbrain_rec_engine_b200 import ScoringEngine, ShardedSearch, shard_bounds, slice_bounds  # noqa: E402
 from brickbrain_rec_engine_b200 import _lib as L  # noqa: E402
 
 
@@ -28,7 +29,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
     n, d, f, b, k = int(os.environ.get("SC_N", "400000")), 384, 64, int(os.environ.get("SC_B", "1024")), 100
     themes = synth.themes_table()
     emb = synth.embeddings(n, d, 3, "aniso")
@@ -36,7 +38,9 @@ def main():
     parts, year, theme = synth.metadata(n, 5, themes)
     q = synth.embeddings(b, d, 6, "aniso") * 2.5
     u = synth.cf_factors(b, f, 7)
-    self_id = np.random.default_rng(8).integers(0, n, b).astype(np.int32)
+    rng = np.random.default_rng(8)
+    self_id = rng.integers(0, n, b).astype(np.int32)
+    rated = [np.sort(rng.choice(n, 40, replace=False)).astype(np.int32) for _ in range(b)]
     cons = np.zeros(4, dtype=L.CONSTRAINT_DTYPE)
     cons[:] = L.no_constraint()
     cons[1]["parts_min"], cons[1]["parts_max"] = 200, 900
@@ -46,36 +50,55 @@ def main():
 
     full = ScoringEngine(n, d, f, device=local, max_batch=b)
     full.load_catalog(emb=emb, item_factors=itf, num_parts=parts, year=year, theme_id=theme)
+    full.set_exclusion_lists(rated)
     lo, hi = shard_bounds(n, world, rank)
     part = ScoringEngine(hi - lo, d, f, device=local, id_offset=lo, max_batch=b)
     part.load_catalog(emb=emb[lo:hi], item_factors=itf[lo:hi], num_parts=parts[lo:hi], year=year[lo:hi], theme_id=theme[lo:hi])
-    kw = dict(q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6, constraints=cons, constraint_index=cidx, self_id=self_id)
+    part.set_exclusion_lists(rated)
+    base = dict(q_cf=u, w_content=0.4, w_cf=0.6, constraints=cons, constraint_index=cidx, self_id=self_id,
+                excl_lists=np.arange(b, dtype=np.int32))
+    forms = {"q_emb": dict(base, q_emb=q), "q_item": dict(base, q_item=self_id)}
 
     ok = True
-    plain = ShardedSearch(part, share_thresholds=False)
-    shared = ShardedSearch(part, share_thresholds=True)
-    assert shared.shared, "threshold handles were not exchanged"
-    for prec in ("fp32", "bf16_rescore"):
-        fs, fi = full.search(k, precision=prec, **kw)
-        ref_s, ref_i = full.search(k, precision="fp32", **kw) if prec != "fp32" else (fs, fi)
-        stats = {}
-        for name, ss in (("plain", plain), ("shared", shared), ("shared-again", shared)):
-            s, i = ss.search(k, precision=prec, **kw)
-            stats[name] = part.info()["last_candidates"]
-            if prec == "fp32":
-                same = np.array_equal(i, fi) and np.array_equal(s, fs)
-            else:
-                rec = np.mean([len(set(i[r]) & set(ref_i[r])) / k for r in range(b)])
-                m = i == ref_i
-                same = rec >= 0.999 and np.allclose(s[m], ref_s[m], rtol=1e-5, atol=2e-6)
-            if not same:
+    p2p = ShardedSearch(part, exchange="p2p")
+    nccl = ShardedSearch(part, exchange="nccl", share_thresholds=False)
+    nccl_shared = ShardedSearch(part, exchange="nccl", share_thresholds=True)
+    assert p2p.exchange == "p2p", "communication blocks were not exchanged"
+    s_lo, s_hi = slice_bounds(b, world, rank)
+
+    def same(prec, s, i, fs, fi, ref_i, ref_s):
+        s, i = (x.cpu().numpy() if torch.is_tensor(x) else x for x in (s, i))
+        if prec == "fp32":
+            return np.array_equal(i, fi) and np.array_equal(s, fs)
+        rec = np.mean([len(set(i[r]) & set(ref_i[r])) / k for r in range(i.shape[0])]) if i.shape[0] else 1.0
+        m = i == ref_i
+        return rec >= 0.999 and np.allclose(s[m], ref_s[m], rtol=1e-5, atol=2e-6)
+
+    for form, kw in forms.items():
+        for prec in ("fp32", "bf16_rescore"):
+            fs, fi = full.search(k, precision=prec, **kw)
+            ref_s, ref_i = full.search(k, precision="fp32", **kw) if prec != "fp32" else (fs, fi)
+            stats = {}
+            for name, ss, result in (("nccl", nccl, "full"), ("nccl+union", nccl_shared, "full"), ("p2p", p2p, "full"),
+                                     ("p2p-slice", p2p, "slice"), ("p2p-again", p2p, "slice")):
+                s, i = ss.search(k, precision=prec, result=result, **kw)
+                stats[name] = part.info()["last_appends"]
+                sl = slice(None) if result == "full" else slice(s_lo, s_hi)
+                if not same(prec, s, i, fs[sl], fi[sl], ref_i[sl], ref_s[sl]):
+                    ok = False
+                    print(f"[rank {rank}] MISMATCH {form} {prec} {name}", flush=True)
+            # device-resident inputs through the p2p exchange
+            kw_dev = {kk: (torch.from_numpy(np.ascontiguousarray(vv)).to(dev) if isinstance(vv, np.ndarray) and kk != "constraints" else vv)
+                      for kk, vv in kw.items()}
+            s, i = p2p.search(k, precision=prec, result="slice", **kw_dev)
+            if not same(prec, s, i, fs[s_lo:s_hi], fi[s_lo:s_hi], ref_i[s_lo:s_hi], ref_s[s_lo:s_hi]):
                 ok = False
-                print(f"[rank {rank}] MISMATCH {prec} {name}", flush=True)
-        # an unflagged search in between must not disturb the collective sequence
-        if rank == 0:
-            part.search(k, precision=prec, **kw)
-        print(f"[rank {rank}] {prec}: candidates inserted per search {stats}", flush=True)
-    flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+                print(f"[rank {rank}] MISMATCH {form} {prec} p2p device inputs", flush=True)
+            # an unflagged search in between must not disturb the collective sequence
+            if rank == 0:
+                part.search(k, precision=prec, **{kk: vv for kk, vv in kw.items() if kk != "q_item"}, **({"q_emb": q} if form == "q_item" else {}))
+            print(f"[rank {rank}] {form} {prec}: candidates appended by this shard's scan {stats}", flush=True)
+    flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
         print("SHARD_CHECK " + ("OK" if flag.item() == 0 else "FAILED"), flush=True)
