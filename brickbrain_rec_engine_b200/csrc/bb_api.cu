@@ -315,17 +315,23 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   if (s_lo < s_fill) s_lo = s_fill;
   if (s_lo < 1) s_lo = 1;
   if (s_lo > s_cap) s_lo = s_cap;
+  // Cost of a static round-robin schedule in tile times: rounds x (tiles per unit + F), F = the fixed price of a unit
+  // (query operand load, pipeline fill, candidate-stream start and its sorted + published prefix at the end: ~8 tile
+  // times).  Large catalogs: many long units, the term only breaks ties between equally full schedules.  Small
+  // catalogs (25k rows = 99 tiles): ONE round of 64 long units beats two rounds of 144 short ones.
   long long splits = s_lo;
-  double best = -1.0;
-  const long long w_lo = (s_lo - 8 > s_fill) ? s_lo - 8 : (s_fill < s_lo ? s_fill : s_lo);
+  double best = 1e300;
+  long long w_lo = (s_lo - 8 > s_fill) ? s_lo - 8 : (s_fill < s_lo ? s_fill : s_lo);
+  if (tc && w_lo > (s_fill + 1) / 2) w_lo = (s_fill + 1) / 2;
+  if (w_lo < 1) w_lo = 1;
+  const double fixed = 8.0;
   for (long long sc = w_lo; sc <= s_cap && sc <= s_lo + 16; ++sc) {
     const long long units = sc * p.n_qblocks;
     const long long rounds = (units + hw_groups - 1) / hw_groups;
-    // occupancy of the static schedule, with a mild preference for the target unit length
-    const double eff = static_cast<double>(units) / static_cast<double>(rounds * hw_groups) -
-                       0.001 * static_cast<double>(sc > s_lo ? sc - s_lo : s_lo - sc);
-    if (eff > best + 1e-9) {
-      best = eff;
+    const double tiles = static_cast<double>((p.n_tiles + sc - 1) / sc);
+    const double cost = static_cast<double>(rounds) * (tiles + fixed) + 0.001 * static_cast<double>(sc > s_lo ? sc - s_lo : s_lo - sc);
+    if (cost < best - 1e-9) {
+      best = cost;
       splits = sc;
     }
   }
@@ -586,6 +592,12 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
       P.lvl_stride = 0;
     }
     P.wave_counter = w->wave_counter();
+    // A unit ends by sorting its candidate buffer, publishing the sorted prefix and refining the row's threshold across
+    // streams -- for the units that scan the row LATER.  With a single scheduling round (or two, when the pilot pass
+    // already seeded every threshold) there is nobody to learn from it: the merge kernel takes unsorted buffers.
+    const long long rounds = (static_cast<long long>(P.n_units) + plan.n_groups - 1) / (plan.n_groups > 0 ? plan.n_groups : 1);
+    const bool seeded = tc && plan.pilot_tiles > 0;
+    P.skip_unit_end = (!collective && (rounds <= 1 || (seeded && rounds <= 2)) && getenv("BB_UNIT_END") == nullptr) ? 1 : 0;
   }
 
   // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
@@ -1123,6 +1135,11 @@ int k_select(int k, bool rescore) {
   }
   return k_sel;
 }
+// candidates whose score is recomputed in exact fp32: the over-fetch itself (k + 25% + 8), not its rounding up to 32
+int k_rescore(int k, int k_sel) {
+  const int r = k + k / 4 + 8;
+  return r < k_sel ? r : k_sel;
+}
 // Results to the caller: device outputs are written in place (nothing to do); host outputs come back in ONE packed
 // copy ([scores | ids] through the workspace's pinned mirror) followed by the error-flag check.
 struct OutPack {
@@ -1186,7 +1203,7 @@ int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_score
   OutPack o;
   rc = out_prepare(h, w, n, out_scores, out_ids, o);
   if (rc != BB_OK) return rc;
-  BB_CUDA(h, launch_merge_emit(P, k, rescore, static_cast<const float*>(w->q_f32.p), h->cat_f32,
+  BB_CUDA(h, launch_merge_emit(P, k, rescore ? k_rescore(k, k_sel) : 0, static_cast<const float*>(w->q_f32.p), h->cat_f32,
                                (q->flags & BB_Q_SCORES_AS_L2) != 0, o.d_scores, o.d_ids, nullptr, stream));
   h->launches++;
   return out_finish(h, w, n, out_scores, out_ids, o, stream);
@@ -1232,11 +1249,12 @@ int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* s
   const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
   ScanParams P;
   Plan plan;
-  rc = run_scan(h, w, q, k_select(k, rescore), nullptr, stream, P, plan, true);
+  const int k_sel = k_select(k, rescore);
+  rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan, true);
   if (rc != BB_OK) return rc;
   CommParams C;
   comm_params(h, slice, static_cast<int>(P.epoch & 1u), C);
-  BB_CUDA(h, launch_merge_emit(P, k, rescore, static_cast<const float*>(w->q_f32.p), h->cat_f32, false, nullptr, nullptr, &C, stream));
+  BB_CUDA(h, launch_merge_emit(P, k, rescore ? k_rescore(k, k_sel) : 0, static_cast<const float*>(w->q_f32.p), h->cat_f32, false, nullptr, nullptr, &C, stream));
   h->launches++;
   int n_mine = B - h->comm_rank * slice;
   if (n_mine > slice) n_mine = slice;

@@ -288,16 +288,20 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
   }
   __syncthreads();
 
-  if (rescore) {
+  if (rescore > 0) {
+    // `rescore` = number of best candidates (by bf16 score) that are re-scored; the rest of the over-fetch only existed
+    // because buffers are kept in multiples of 32 and is dropped here.
+    for (int c = rescore + threadIdx.x; c < kMaxSel; c += blockDim.x) stage[c] = 0ull;
+    __syncthreads();
     // exact fp32 dot of the query operand with each surviving catalog row.  Eight lanes per candidate, four
     // candidates per warp at a time: every lane keeps up to 14 independent 16-byte gathers in flight, which is what
     // hides the latency of these scattered row reads.
     const float4* qv = reinterpret_cast<const float4*>(q_f32 + static_cast<int64_t>(q) * P.k_pad);
     const int n4 = P.k_pad >> 2;
     const int sub = lane >> 3, l8 = lane & 7;
-    for (int c0 = warp * 4; c0 < kMaxSel; c0 += 16) {
+    for (int c0 = warp * 4; c0 < rescore; c0 += 16) {
       const int c = c0 + sub;
-      const uint64_t key = stage[c];
+      const uint64_t key = c < rescore ? stage[c] : 0ull;
       float acc = 0.f;
       int32_t gid = -1;
       if (key != 0ull) {
@@ -466,8 +470,9 @@ seed_thresholds_kernel(const ScanParams P, int64_t pilot_items) {
   }
   mg.flush();
   // listed ids inside the pilot range (they may sit behind up to E of the maxima)
+  // (a single list per query is walked exactly by the pilot's epilogue: nothing to allow for)
   int64_t excl = 0;
-  if (lane == 0 && P.q_excl_n > 0) {
+  if (lane == 0 && P.q_excl_n > 1) {
     for (int e = 0; e < P.q_excl_n; ++e) {
       const int32_t l = __ldg(P.q_excl + static_cast<int64_t>(row) * P.q_excl_n + e);
       if (l < 0) continue;
@@ -635,13 +640,13 @@ cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bi
   return cudaGetLastError();
 }
 
-cudaError_t launch_merge_emit(const ScanParams& P, int k, bool rescore, const float* q_f32, const float* cat_f32,
+cudaError_t launch_merge_emit(const ScanParams& P, int k, int rescore, const float* q_f32, const float* cat_f32,
                               bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream) {
   if (comm != nullptr) {
-    merge_emit_kernel<true><<<P.n_queries, 128, 0, stream>>>(P, k, rescore ? 1 : 0, q_f32, cat_f32, 0, nullptr, nullptr, *comm);
+    merge_emit_kernel<true><<<P.n_queries, 128, 0, stream>>>(P, k, rescore, q_f32, cat_f32, 0, nullptr, nullptr, *comm);
   } else {
     CommParams none{};
-    merge_emit_kernel<false><<<P.n_queries, 128, 0, stream>>>(P, k, rescore ? 1 : 0, q_f32, cat_f32, as_l2 ? 1 : 0, out_scores,
+    merge_emit_kernel<false><<<P.n_queries, 128, 0, stream>>>(P, k, rescore, q_f32, cat_f32, as_l2 ? 1 : 0, out_scores,
                                                               out_ids, none);
   }
   return cudaGetLastError();

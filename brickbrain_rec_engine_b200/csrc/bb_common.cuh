@@ -162,6 +162,7 @@ struct ScanParams {
   float* pilot_max;
   int32_t pilot_groups;
   int32_t pilot_mode;                // 1 = this launch is the pilot pass
+  int32_t skip_unit_end;             // 1 = units do not sort / publish / refine at their end (no later unit would use it)
   // schedule
   int32_t n_qblocks;      // query blocks
   int32_t n_splits;       // catalog splits (units = n_qblocks * n_splits)

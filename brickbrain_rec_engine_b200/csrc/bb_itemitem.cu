@@ -2,33 +2,105 @@
 // the schema stub is src/db/user_interaction_schema.sql:136-145): cosine between
 // item columns of the sparse user x item rating matrix, top-k neighbours per item.
 //
-// Two paths.  Catalog-sized item sets (N*N*4 B <= 6 GiB, e.g. the reference's 25,216 sets = 2.5 GB) take the
-// dense-Gram path below (global fire-and-forget reductions + one streaming select pass).  Larger item sets take
-// the accumulator path, where the N x N Gram matrix is never materialized:
-//   1. CSR -> CSC on device (histogram, scan, scatter) + column square norms,
-//   2. items ordered by descending degree bucket (hot columns first: LPT balance),
-//   3. one CTA per item i: a shared-memory accumulator over all items j receives
-//      r_ui * r_uj for every user u that rated i (shared-memory atomics; integer
-//      ratings make the sums exact and order independent), then the same CTA
-//      normalizes and selects the top-k without the row ever reaching HBM.
-// Algorithmic work (sparse): sum_u nnz_u^2 multiply-adds; bytes >= nnz * 8.
+// The N x N Gram matrix is never materialized.  Pipeline (all on the device):
+//   1. CSR -> CSC with a multi-block counting sort: every CTA owns a contiguous user range, histograms its ratings per
+//      item in SHARED memory, a column scan turns the per-CTA histograms into per-CTA write cursors, and the CTAs
+//      scatter (user, rating) with shared-memory cursors.  No global atomic ever lands on a hot item's counter (a
+//      Zipf catalog sends ~1M ratings to its most popular item; the first version serialized on that address).
+//      Catalogs whose histogram does not fit in shared memory (> ~56k items) use global-atomic kernels instead.
+//   2. work units = (item i, chunk of <= C of i's raters), hot items first (LPT).  One CTA per unit: a dense
+//      shared-memory accumulator over all items j receives r_ui * r_uj for every rater u of the chunk (1024 threads:
+//      a warp fetches 32 raters' row bounds at once, then walks the rows with coalesced reads; shared-memory float
+//      atomics; integer ratings keep the sums exact and order independent).
+//   3. an item with ONE unit is normalized and selected straight from shared memory; a hot item's units add their
+//      partial rows to a global row buffer (coalesced fire-and-forget reductions) and the unit that finishes last
+//      selects from it.
+// Algorithmic work (sparse): sum_u nnz_u^2 multiply-adds; bytes >= nnz * 8.  The first version (global reductions into
+// a dense 2.5 GB Gram + a streaming select) took 27.5 ms at 1M users x 25,216 items and was bound by same-address
+// atomics; this one is bound by shared-memory atomic throughput.
 #include "bb_common.cuh"
 #include "bb_kernels.h"
 
 namespace bb {
 namespace {
 
-constexpr int kIIThreads = 256;
-constexpr int kIIWarps = kIIThreads / 32;
+constexpr int kAccThreads = 1024;                 // threads of the accumulate / sort CTAs (latency-bound gathers: more warps in flight)
+constexpr int kAccWarps = kAccThreads / 32;
+constexpr int kSortCtas = 148;                    // CTAs of the counting sort (one per SM)
+constexpr int kSmemHistItems = 56 * 1024;         // largest item count whose uint32 histogram fits in shared memory
 
-__global__ void ii_hist_kernel(const int32_t* __restrict__ indices, const float* __restrict__ values, int64_t nnz,
-                               unsigned long long* __restrict__ col_cnt, float* __restrict__ sq) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= nnz) return;
-  const int32_t c = indices[i];
-  atomicAdd(col_cnt + c, 1ull);
-  const float v = values[i];
-  atomicAdd(sq + c, v * v);
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ 1. CSR -> CSC (counting sort)
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* a, int64_t n, int64_t v) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// users [u0, u1) of sort CTA g: ranges balanced by rating count
+__device__ __forceinline__ void sort_user_range(const int64_t* indptr, int64_t n_users, int64_t nnz, int g, int64_t& u0, int64_t& u1) {
+  const int64_t t0 = nnz * g / kSortCtas, t1 = nnz * (g + 1) / kSortCtas;
+  u0 = g == 0 ? 0 : lower_bound_i64(indptr, n_users + 1, t0);
+  u1 = g == kSortCtas - 1 ? n_users : lower_bound_i64(indptr, n_users + 1, t1);
+  if (u0 > n_users) u0 = n_users;
+  if (u1 > n_users) u1 = n_users;
+}
+
+__global__ void __launch_bounds__(kAccThreads)
+ii_block_hist_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                     int64_t n_users, int64_t nnz, int n_items, uint32_t* __restrict__ block_hist, float* __restrict__ block_sq,
+                     int* __restrict__ value_flags) {
+  extern __shared__ __align__(16) unsigned char ii_smem[];
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ii_smem);            // [n_items]
+  float* sqs = reinterpret_cast<float*>(ii_smem) + n_items;         // [n_items]
+  for (int i = threadIdx.x; i < n_items; i += kAccThreads) { hist[i] = 0u; sqs[i] = 0.f; }
+  __syncthreads();
+  int64_t u0, u1;
+  sort_user_range(indptr, n_users, nnz, blockIdx.x, u0, u1);
+  const int64_t e0 = __ldg(indptr + u0), e1 = __ldg(indptr + u1);
+  bool odd = false;                                 // a rating that is not an integer in [0, 1024]
+  float vmax = 0.f;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += kAccThreads) {
+    const int32_t c = __ldg(indices + e);
+    const float v = __ldg(values + e);
+    atomicAdd(hist + c, 1u);
+    atomicAdd(sqs + c, v * v);
+    odd |= !(v >= 0.f && v <= 1024.f && v == floorf(v));
+    vmax = fmaxf(vmax, v);
+  }
+  if (__any_sync(kFull, odd) && (threadIdx.x & 31) == 0) atomicOr(value_flags, 1);
+  vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, 16));
+  vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, 8));
+  vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, 4));
+  vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, 2));
+  vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, 1));
+  if ((threadIdx.x & 31) == 0 && !odd) atomicMax(value_flags + 1, static_cast<int>(vmax));
+  if (blockIdx.x == 0 && threadIdx.x == 0) value_flags[2] = 1;      // the flags are valid (this kernel ran)
+  __syncthreads();
+  uint32_t* out = block_hist + static_cast<int64_t>(blockIdx.x) * n_items;
+  float* out_sq = block_sq + static_cast<int64_t>(blockIdx.x) * n_items;
+  for (int i = threadIdx.x; i < n_items; i += kAccThreads) { out[i] = hist[i]; out_sq[i] = sqs[i]; }
+}
+
+// per item: total count and square norm; the per-CTA histograms become per-CTA exclusive prefixes (relative to the
+// item's column start)
+__global__ void ii_column_prefix_kernel(uint32_t* __restrict__ block_hist, const float* __restrict__ block_sq, int n_items,
+                                        unsigned long long* __restrict__ col_cnt, float* __restrict__ sq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  uint32_t run = 0u;
+  float s = 0.f;
+  for (int g = 0; g < kSortCtas; ++g) {
+    const uint32_t c = block_hist[static_cast<int64_t>(g) * n_items + i];
+    block_hist[static_cast<int64_t>(g) * n_items + i] = run;
+    run += c;
+    s += block_sq[static_cast<int64_t>(g) * n_items + i];
+  }
+  col_cnt[i] = run;
+  sq[i] = sqrtf(s);                               // the item's L2 norm (what the cosine divides by)
 }
 
 // single-block exclusive scan (n_items is catalog sized; this is microseconds)
@@ -51,26 +123,66 @@ __global__ void ii_scan_kernel(const unsigned long long* __restrict__ cnt, int n
   long long run = part[t];
   for (int i = lo; i < hi; ++i) {
     ptr[i] = run;
-    cursor[i] = static_cast<unsigned long long>(run);
+    if (cursor != nullptr) cursor[i] = static_cast<unsigned long long>(run);
     run += static_cast<long long>(cnt[i]);
   }
 }
 
+__global__ void __launch_bounds__(kAccThreads)
+ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                        int64_t n_users, int64_t nnz, int n_items, const uint32_t* __restrict__ block_hist,
+                        const long long* __restrict__ col_ptr, int2* __restrict__ csc) {
+  extern __shared__ __align__(16) unsigned char ii_smem[];
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(ii_smem);          // [n_items]: this CTA's next slot inside every column
+  const uint32_t* mine = block_hist + static_cast<int64_t>(blockIdx.x) * n_items;
+  for (int i = threadIdx.x; i < n_items; i += kAccThreads) cursor[i] = mine[i];
+  __syncthreads();
+  int64_t u0, u1;
+  sort_user_range(indptr, n_users, nnz, blockIdx.x, u0, u1);
+  // one thread per rating; its user is found by a search in the CTA's slice of indptr (rows are ~20 long: a warp per
+  // user would leave a third of the lanes idle and chain two dependent loads per row)
+  const int64_t e0 = __ldg(indptr + u0), e1 = __ldg(indptr + u1);
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += kAccThreads) {
+    int64_t lo = u0, hi = u1;                       // largest u with indptr[u] <= e
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(indptr + mid) <= e) lo = mid; else hi = mid;
+    }
+    const int32_t c = __ldg(indices + e);
+    const long long pos = __ldg(col_ptr + c) + atomicAdd(cursor + c, 1u);
+    csc[pos] = make_int2(static_cast<int32_t>(lo), __float_as_int(__ldg(values + e)));
+  }
+}
+
+__global__ void ii_sqrt_kernel(float* __restrict__ sq, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sq[i] = sqrtf(sq[i]);
+}
+
+// ---- fallback for catalogs whose histogram does not fit in shared memory: global atomics
+__global__ void ii_hist_kernel(const int32_t* __restrict__ indices, const float* __restrict__ values, int64_t nnz,
+                               unsigned long long* __restrict__ col_cnt, float* __restrict__ sq) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nnz) return;
+  const int32_t c = indices[i];
+  atomicAdd(col_cnt + c, 1ull);
+  const float v = values[i];
+  atomicAdd(sq + c, v * v);
+}
 __global__ void ii_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                   const float* __restrict__ values, int64_t n_users,
-                                  unsigned long long* __restrict__ cursor, int32_t* __restrict__ csc_user,
-                                  float* __restrict__ csc_val) {
+                                  unsigned long long* __restrict__ cursor, int2* __restrict__ csc) {
   const int lane = threadIdx.x & 31;
   const int64_t u = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (u >= n_users) return;
   for (int64_t e = indptr[u] + lane; e < indptr[u + 1]; e += 32) {
     const unsigned long long pos = atomicAdd(cursor + indices[e], 1ull);
-    csc_user[pos] = static_cast<int32_t>(u);
-    csc_val[pos] = values[e];
+    csc[pos] = make_int2(static_cast<int32_t>(u), __float_as_int(values[e]));
   }
 }
 
-// order items by descending floor(log2(degree+1)) bucket
+// ------------------------------------------------------------------ 2. work units
+// items ordered by descending floor(log2(degree+1)) bucket (hot columns first: LPT balance)
 __global__ void ii_bucket_count_kernel(const unsigned long long* __restrict__ cnt, int n, int* __restrict__ bucket_cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -90,28 +202,107 @@ __global__ void ii_bucket_scatter_kernel(const unsigned long long* __restrict__ 
   const int b = 63 - __clzll(static_cast<long long>(cnt[i]) + 1);
   order[atomicAdd(bucket_pos + (63 - b), 1)] = i;
 }
+// unit_off[p] = first unit of the p-th item of `order`; hot_of[item] = row of the item in the partial-row buffer
+// (-1 for single-unit items).  counters[0] = number of units, counters[1] = number of hot items.  Single block.
+__global__ void ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* __restrict__ order, int n,
+                                int chunk, int* __restrict__ unit_off, int* __restrict__ hot_of, int* __restrict__ counters) {
+  __shared__ int part_u[1024], part_h[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int lo = t * per, hi = min(n, lo + per);
+  int su = 0, sh = 0;
+  for (int p = lo; p < hi; ++p) {
+    const long long d = static_cast<long long>(col_cnt[order[p]]);
+    const int units = d <= chunk ? 1 : static_cast<int>((d + chunk - 1) / chunk);
+    su += units;
+    sh += units > 1;
+  }
+  part_u[t] = su;
+  part_h[t] = sh;
+  __syncthreads();
+  if (t == 0) {
+    int ru = 0, rh = 0;
+    for (int i = 0; i < 1024; ++i) {
+      const int u = part_u[i], h = part_h[i];
+      part_u[i] = ru; part_h[i] = rh;
+      ru += u; rh += h;
+    }
+    counters[0] = ru;
+    counters[1] = rh;
+    unit_off[n] = ru;
+    // integer accumulators are exact while vmax^2 * (largest degree) stays below 2^31
+    // (order[0] lies in the top floor(log2(degree + 1)) bucket: no degree exceeds twice its own + 1)
+    const long long dmax = n > 0 ? 2 * (static_cast<long long>(col_cnt[order[0]]) + 1) : 1;
+    const long long vm = counters[5];
+    counters[3] = (counters[4] == 0 && counters[6] == 1 && vm * vm * dmax < (1ll << 31)) ? 1 : 0;
+  }
+  __syncthreads();
+  int ru = part_u[t], rh = part_h[t];
+  for (int p = lo; p < hi; ++p) {
+    const int item = order[p];
+    const long long d = static_cast<long long>(col_cnt[item]);
+    const int units = d <= chunk ? 1 : static_cast<int>((d + chunk - 1) / chunk);
+    unit_off[p] = ru;
+    hot_of[item] = units > 1 ? rh : -1;
+    ru += units;
+    rh += units > 1;
+  }
+}
 
+__global__ void ii_zero_hot_kernel(float* __restrict__ hot_rows, int* __restrict__ hot_done, const int* __restrict__ counters,
+                                   int n_items, int max_hot) {
+  const int n_hot = min(counters[1], max_hot);
+  const int64_t total = static_cast<int64_t>(n_hot) * n_items;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    hot_rows[i] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hot; i += gridDim.x * blockDim.x) hot_done[i] = 0;
+}
+
+// ------------------------------------------------------------------ 3. accumulate + select
 struct IIMerger {          // per-warp running top-128 (same scheme as the scan merge)
   uint64_t* stage;
-  int n_new;
+  int n_new, n_sorted;     // new keys at stage[128 + ...], sorted keys at stage[0 ...]
   int lane;
   uint64_t floor_key;      // keys below the current 128th best are dropped early
   __device__ void init(uint64_t* s, int l) {
-    stage = s; n_new = 0; lane = l; floor_key = 0;
-    for (int i = lane; i < kCap; i += 32) stage[i] = 0ull;
+    stage = s; n_new = 0; n_sorted = 0; lane = l; floor_key = 0;
+    for (int i = lane; i < kCap / 2; i += 32) stage[i] = 0ull;      // (the tree merge reads whole prefixes)
+    __syncwarp();
+  }
+  // Sorts [sorted prefix | new keys] and keeps the best 128.  The sort network is sized to the number of keys that are
+  // actually there (a cold item leaves a few dozen keys per warp: a 64-key network is 8x cheaper than the 256-key one).
+  template <int E>
+  __device__ void flush_n(int n_keys) {
+    // gather the n_keys live keys (prefix [0, n_sorted) and new [128, 128 + n_new)) into E registers per lane
+    uint64_t v[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int e = (i << 5) | lane;
+      v[i] = e < n_sorted ? stage[e] : (e < n_keys ? stage[kCap / 2 + (e - n_sorted)] : 0ull);
+    }
+    __syncwarp();
+    warp_sort_desc<E>(v, lane);
+#pragma unroll
+    for (int i = 0; i < E; ++i)
+      if (i < kEpl / 2) stage[(i << 5) | lane] = v[i];
+    if (E < kEpl / 2) {
+#pragma unroll
+      for (int i = E; i < kEpl / 2; ++i) stage[(i << 5) | lane] = 0ull;
+    }
+    n_sorted = n_keys < kCap / 2 ? n_keys : kCap / 2;
+    uint64_t kth = 0ull;
+    if (E >= kEpl / 2) kth = __shfl_sync(kFull, v[kEpl / 2 - 1], 31);
+    floor_key = kth;                                 // 0 while fewer than 128 keys are held
+    n_new = 0;
     __syncwarp();
   }
   __device__ void flush() {
-    uint64_t v[kEpl];
-#pragma unroll
-    for (int i = 0; i < kEpl; ++i) v[i] = stage[(i << 5) | lane];
-    __syncwarp();
-    warp_sort_desc<kEpl>(v, lane);
-#pragma unroll
-    for (int i = 0; i < kEpl; ++i) stage[(i << 5) | lane] = (i < kEpl / 2) ? v[i] : 0ull;
-    floor_key = __shfl_sync(kFull, v[kEpl / 2 - 1], 31);
-    n_new = 0;
-    __syncwarp();
+    const int n_keys = n_sorted + n_new;
+    if (n_new == 0) return;
+    if (n_keys <= 32) flush_n<1>(n_keys);
+    else if (n_keys <= 64) flush_n<2>(n_keys);
+    else if (n_keys <= 128) flush_n<4>(n_keys);
+    else flush_n<kEpl>(n_keys);
   }
   __device__ void offer(uint64_t key) {
     if (key <= floor_key) key = 0ull;
@@ -122,240 +313,253 @@ struct IIMerger {          // per-warp running top-128 (same scheme as the scan 
     __syncwarp();
     if (n_new + 32 > kCap / 2) flush();
   }
+  // top-128 of this merger's sorted prefix and another warp's sorted prefix (one step of the tree merge)
+  __device__ void absorb_sorted(const uint64_t* other) {
+    constexpr int PE = kEpl / 2;
+    uint64_t p[PE];
+#pragma unroll
+    for (int i = 0; i < PE; ++i) {
+      const int e = (i << 5) | lane;
+      const uint64_t r = other[kCap / 2 - 1 - e];
+      const uint64_t a = stage[e];
+      p[i] = a > r ? a : r;
+    }
+    __syncwarp();
+    warp_bitonic_merge_desc<PE>(p, lane);
+#pragma unroll
+    for (int i = 0; i < PE; ++i) stage[(i << 5) | lane] = p[i];
+    __syncwarp();
+  }
 };
 
-__global__ void __launch_bounds__(kIIThreads)
-ii_main_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-               const long long* __restrict__ col_ptr, const int32_t* __restrict__ csc_user,
-               const float* __restrict__ csc_val, const float* __restrict__ sq, const int32_t* __restrict__ order,
-               int n_items, int range, int k, int* __restrict__ work_counter, float* __restrict__ out_scores,
-               int32_t* __restrict__ out_ids) {
+// normalize + select the range [j0, j1) of item i's Gram row (`row` in shared or global memory) into the warp mergers.
+// Four strides per step: the norm loads of the four keys are independent of the mergers' state and overlap.
+template <bool kGlobal, bool kInt>
+__device__ __forceinline__ void ii_select_range(const float* row, int i, float norm_i, const float* __restrict__ norm, int j0, int j1,
+                                                IIMerger& mg, int warp, int lane) {
+  constexpr int U = 4;
+  const int n = j1 - j0;
+  for (int base = warp * 32; base < n; base += kAccThreads * U) {
+    uint64_t key[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int jj = base + u * kAccThreads + lane;
+      key[u] = 0ull;
+      if (jj < n) {
+        const float g = kGlobal ? __ldcg(row + jj) : (kInt ? static_cast<float>(reinterpret_cast<const unsigned*>(row)[jj]) : row[jj]);
+        const int j = j0 + jj;
+        if (g > 0.f && j != i) key[u] = make_key(g / (norm_i * __ldg(norm + j)), static_cast<uint32_t>(j));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) mg.offer(key[u]);
+  }
+}
+
+// Tree merge of the kAccWarps sorted per-warp tops (all warps call; ends with the CTA's top-128 in stages[0..127]).
+__device__ __forceinline__ void ii_tree_merge(uint64_t* stages, IIMerger& mg, int warp) {
+#pragma unroll 1
+  for (int s = 1; s < kAccWarps; s <<= 1) {
+    __syncthreads();
+    if ((warp & (2 * s - 1)) == 0) mg.absorb_sorted(stages + (warp + s) * kCap);
+  }
+  __syncthreads();
+}
+
+// warp 0 writes item i's lists from the CTA's sorted top (stages[0..127]): positives first, then zero-similarity items
+// by ascending id
+__device__ __forceinline__ void ii_emit(const uint64_t* s0, int i, int n_items, int k, int lane, float* __restrict__ out_scores,
+                                        int32_t* __restrict__ out_ids) {
+  int n_pos = 0;
+  for (int x = 0; x < k; x += 32) {
+    const uint64_t key = (x + lane < k) ? s0[x + lane] : 0ull;
+    n_pos += __popc(__ballot_sync(kFull, key != 0ull));
+    if (x + lane < k && key != 0ull) {
+      out_scores[static_cast<int64_t>(i) * k + x + lane] = key_score(key);
+      out_ids[static_cast<int64_t>(i) * k + x + lane] = key_id(key);
+    }
+  }
+  if (n_pos < k && lane == 0) {
+    int filled = n_pos;
+    for (int j = 0; j < n_items && filled < k; ++j) {
+      if (j == i) continue;
+      bool used = false;
+      for (int x = 0; x < n_pos; ++x) used |= (key_id(s0[x]) == j);
+      if (used) continue;
+      out_scores[static_cast<int64_t>(i) * k + filled] = 0.f;
+      out_ids[static_cast<int64_t>(i) * k + filled] = j;
+      ++filled;
+    }
+    for (; filled < k; ++filled) {
+      out_scores[static_cast<int64_t>(i) * k + filled] = -INFINITY;
+      out_ids[static_cast<int64_t>(i) * k + filled] = -1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAccThreads)
+ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                     const long long* __restrict__ col_ptr, const int2* __restrict__ csc,
+                     const float* __restrict__ norm, const int32_t* __restrict__ order, const int* __restrict__ unit_off,
+                     const int* __restrict__ hot_of, const int* __restrict__ counters, int n_items, int range, int chunk, int k,
+                     int max_hot, float* __restrict__ hot_rows, int* __restrict__ hot_done, int* __restrict__ work_counter,
+                     float* __restrict__ out_scores, int32_t* __restrict__ out_ids) {
   extern __shared__ __align__(16) unsigned char ii_smem[];
   float* acc = reinterpret_cast<float*>(ii_smem);                                   // [range]
-  uint64_t* stages = reinterpret_cast<uint64_t*>(ii_smem + static_cast<size_t>(range) * 4);   // [kIIWarps][kCap]
-  __shared__ int s_item;
+  uint64_t* stages = reinterpret_cast<uint64_t*>(ii_smem + static_cast<size_t>(range) * 4);   // [kAccWarps][kCap]
+  __shared__ int s_unit, s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_units = counters[0];
+  const bool int_mode = counters[3] != 0;          // every rating is a small non-negative integer (set by ii_units_kernel)
 
   while (true) {
-    if (tid == 0) s_item = atomicAdd(work_counter, 1);
+    if (tid == 0) s_unit = atomicAdd(work_counter, 1);
     __syncthreads();
-    const int slot = s_item;
+    const int unit = s_unit;
     __syncthreads();
-    if (slot >= n_items) break;
-    const int i = order[slot];
-    const float sq_i = sq[i];
+    if (unit >= n_units) break;
+    // unit -> (position in `order`, chunk of the item's raters)
+    int lo = 0, hi = n_items;                      // largest p with unit_off[p] <= unit
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(unit_off + mid) <= unit) lo = mid; else hi = mid;
+    }
+    const int i = __ldg(order + lo);
+    const int c_idx = unit - __ldg(unit_off + lo);
+    const int n_item_units = __ldg(unit_off + lo + 1) - __ldg(unit_off + lo);
+    const long long e_begin = __ldg(col_ptr + i) + static_cast<long long>(c_idx) * chunk;
+    const long long e_end = min(__ldg(col_ptr + i + 1), e_begin + chunk);
+    const int hot = __ldg(hot_of + i);
+    const bool single = n_item_units == 1;
+    const float norm_i = __ldg(norm + i);
     IIMerger mg;
-    mg.init(stages + warp * kCap, lane);
+    if (single) mg.init(stages + warp * kCap, lane);
 
     for (int j0 = 0; j0 < n_items; j0 += range) {
       const int j1 = min(n_items, j0 + range);
-      for (int j = tid; j < j1 - j0; j += kIIThreads) acc[j] = 0.f;
+      for (int j = tid; j < j1 - j0; j += kAccThreads) acc[j] = 0.f;
       __syncthreads();
-      // accumulate r_ui * r_uj for every user of column i (one warp per user)
-      for (long long e = col_ptr[i] + warp; e < col_ptr[i + 1]; e += kIIWarps) {
-        const int32_t u = csc_user[e];
-        const float r_ui = csc_val[e];
-        for (int64_t p = indptr[u] + lane; p < indptr[u + 1]; p += 32) {
-          const int32_t j = indices[p];
-          if (j >= j0 && j < j1) atomicAdd(acc + (j - j0), r_ui * values[p]);
+      // Raters are dealt to the warps cyclically (rater e_begin + x goes to warp x % 32), so an item with a few dozen
+      // raters still keeps every warp busy.  Per step a warp prefetches up to 32 of its raters at once -- lane l holds
+      // (user, rating, row bounds) of one -- then walks those rows one after the other with coalesced row reads; the
+      // loads of row r+1 do not depend on the atomics of row r, so the unrolled loop keeps several rows in flight.
+      const long long n_raters = e_end - e_begin;
+      for (long long x0 = 0; x0 * kAccWarps + warp < n_raters; x0 += 32) {
+        const long long mine = (x0 + lane) * kAccWarps + warp;
+        int64_t p0 = 0;
+        int len = 0;
+        float r_ui = 0.f;
+        if (mine < n_raters) {
+          const int2 ur = __ldg(csc + e_begin + mine);
+          r_ui = __int_as_float(ur.y);
+          p0 = __ldg(indptr + ur.x);
+          len = static_cast<int>(__ldg(indptr + ur.x + 1) - p0);
+        }
+        const int n_r = __popc(__ballot_sync(kFull, mine < n_raters));
+#pragma unroll 4
+        for (int r = 0; r < n_r; ++r) {
+          const int64_t q0 = __shfl_sync(kFull, p0, r);
+          const int ln = __shfl_sync(kFull, len, r);
+          const float rr = __shfl_sync(kFull, r_ui, r);
+          for (int t = lane; t < ln; t += 32) {
+            const int32_t j = __ldg(indices + q0 + t);
+            const float v = __ldg(values + q0 + t);
+            if (j >= j0 && j < j1) {
+              // integral ratings (the usual 1..5 stars): native integer shared-memory atomics; a float atomicAdd on
+              // shared memory is a compare-and-swap loop that spins on popular items
+              if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (j - j0), static_cast<unsigned>(rr * v));
+              else atomicAdd(acc + (j - j0), rr * v);
+            }
+          }
         }
       }
       __syncthreads();
-      // normalize + select: each warp scans a strided slice of the accumulator
-      for (int base = warp * 32; base < j1 - j0; base += kIIThreads) {
-        const int jj = base + lane;
-        uint64_t key = 0ull;
-        if (jj < j1 - j0) {
-          const float g = acc[jj];
-          const int j = j0 + jj;
-          if (g > 0.f && j != i) key = make_key(g / (sqrtf(sq_i) * sqrtf(sq[j])), static_cast<uint32_t>(j));
+      if (single) {
+        if (int_mode) ii_select_range<false, true>(acc, i, norm_i, norm, j0, j1, mg, warp, lane);
+        else ii_select_range<false, false>(acc, i, norm_i, norm, j0, j1, mg, warp, lane);
+      } else if (hot >= 0 && hot < max_hot) {
+        float* row = hot_rows + static_cast<int64_t>(hot) * n_items + j0;
+        for (int j = tid; j < j1 - j0; j += kAccThreads) {
+          const float v = int_mode ? static_cast<float>(reinterpret_cast<const unsigned*>(acc)[j]) : acc[j];
+          if (v != 0.f) atomicAdd(row + j, v);       // coalesced fire-and-forget reductions (result unused -> RED)
         }
-        mg.offer(key);
       }
       __syncthreads();
     }
-    mg.flush();
-    __syncthreads();
-    // warp 0 merges the 8 per-warp tops
-    if (warp == 0) {
-      IIMerger fin;
-      uint64_t* s0 = stages;                       // reuse warp 0's stage as the final one
-      // copy other warps' results through registers, then offer
-      uint64_t mine[kEpl / 2];
-#pragma unroll
-      for (int x = 0; x < kEpl / 2; ++x) mine[x] = s0[(x << 5) | lane];
-      __syncwarp();
-      fin.init(s0, lane);
-#pragma unroll
-      for (int x = 0; x < kEpl / 2; ++x) fin.offer(mine[x]);
-      for (int w = 1; w < kIIWarps; ++w)
-        for (int x = 0; x < kCap / 2; x += 32) fin.offer(stages[w * kCap + x + lane]);
-      fin.flush();
-      // emit: positives first, then zero-similarity items in ascending id order
-      int n_pos = 0;
-      for (int x = 0; x < k; x += 32) {
-        const uint64_t key = (x + lane < k) ? s0[x + lane] : 0ull;
-        n_pos += __popc(__ballot_sync(kFull, key != 0ull));
-        if (x + lane < k && key != 0ull) {
-          out_scores[static_cast<int64_t>(i) * k + x + lane] = key_score(key);
-          out_ids[static_cast<int64_t>(i) * k + x + lane] = key_id(key);
-        }
-      }
-      if (n_pos < k && lane == 0) {
-        int filled = n_pos;
-        for (int j = 0; j < n_items && filled < k; ++j) {
-          if (j == i) continue;
-          bool used = false;
-          for (int x = 0; x < n_pos; ++x) used |= (key_id(s0[x]) == j);
-          if (used) continue;
-          out_scores[static_cast<int64_t>(i) * k + filled] = 0.f;
-          out_ids[static_cast<int64_t>(i) * k + filled] = j;
-          ++filled;
-        }
-        for (; filled < k; ++filled) {
-          out_scores[static_cast<int64_t>(i) * k + filled] = -INFINITY;
-          out_ids[static_cast<int64_t>(i) * k + filled] = -1;
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
 
-// ---------------------------------------------------------------- dense-Gram path (catalog-sized item sets)
-// For N items with N*N*4 B within budget the Gram matrix G = X^T X is accumulated in HBM with fire-and-forget
-// global reductions (RED.ADD.F32: ~1 per lane per cycle per SM, no serialization behind hot items), one warp per
-// user: every ordered pair (a, b) of the user's rated items adds r_a * r_b to G[a][b].  A second kernel streams
-// each row once (coalesced), normalizes by the diagonal and selects the top-k.  Integer ratings keep every partial
-// sum exact (< 2^24), so the result does not depend on the order of the atomics.
-__global__ void __launch_bounds__(256)
-ii_gram_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-               int64_t n_users, int n_items, float* __restrict__ gram) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t u = warp0; u < n_users; u += n_warps) {
-    const int64_t lo = indptr[u], hi = indptr[u + 1];
-    const int d = static_cast<int>(hi - lo);
-    // pairs (a, b): lanes sweep the flattened d*d index space
-    for (int p = lane; p < d * d; p += 32) {
-      const int a = p / d, b = p - a * d;
-      const int32_t ia = __ldg(indices + lo + a), ib = __ldg(indices + lo + b);
-      atomicAdd(gram + static_cast<int64_t>(ia) * n_items + ib, __ldg(values + lo + a) * __ldg(values + lo + b));
+    if (single) {
+      mg.flush();
+      ii_tree_merge(stages, mg, warp);
+      if (warp == 0) ii_emit(stages, i, n_items, k, lane, out_scores, out_ids);
+      __syncthreads();
+    } else {
+      // the unit of a hot item that finishes last selects from the completed global row
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_last = (atomicAdd(hot_done + hot, 1) == n_item_units - 1);
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        mg.init(stages + warp * kCap, lane);
+        ii_select_range<true, false>(hot_rows + static_cast<int64_t>(hot) * n_items, i, norm_i, norm, 0, n_items, mg, warp, lane);
+        mg.flush();
+        ii_tree_merge(stages, mg, warp);
+        if (warp == 0) ii_emit(stages, i, n_items, k, lane, out_scores, out_ids);
+      }
+      __syncthreads();
     }
   }
 }
 
-__global__ void __launch_bounds__(kIIThreads)
-ii_select_kernel(const float* __restrict__ gram, int n_items, int k, float* __restrict__ out_scores,
-                 int32_t* __restrict__ out_ids) {
-  __shared__ uint64_t stages[kIIWarps * kCap];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
-    const float* row = gram + static_cast<int64_t>(i) * n_items;
-    const float sq_i = row[i];
-    IIMerger mg;
-    mg.init(stages + warp * kCap, lane);
-    for (int base = warp * 32; base < n_items; base += kIIThreads) {
-      const int j = base + lane;
-      uint64_t key = 0ull;
-      if (j < n_items) {
-        const float g = __ldg(row + j);
-        if (g > 0.f && j != i) key = make_key(g / (sqrtf(sq_i) * sqrtf(__ldg(gram + static_cast<int64_t>(j) * n_items + j))), static_cast<uint32_t>(j));
-      }
-      mg.offer(key);
-    }
-    mg.flush();
-    __syncthreads();
-    if (warp == 0) {
-      uint64_t* s0 = stages;
-      uint64_t mine[kEpl / 2];
-#pragma unroll
-      for (int x = 0; x < kEpl / 2; ++x) mine[x] = s0[(x << 5) | lane];
-      __syncwarp();
-      IIMerger fin;
-      fin.init(s0, lane);
-#pragma unroll
-      for (int x = 0; x < kEpl / 2; ++x) fin.offer(mine[x]);
-      for (int w = 1; w < kIIWarps; ++w)
-        for (int x = 0; x < kCap / 2; x += 32) fin.offer(stages[w * kCap + x + lane]);
-      fin.flush();
-      int n_pos = 0;
-      for (int x = 0; x < k; x += 32) {
-        const uint64_t key = (x + lane < k) ? s0[x + lane] : 0ull;
-        n_pos += __popc(__ballot_sync(kFull, key != 0ull));
-        if (x + lane < k && key != 0ull) {
-          out_scores[static_cast<int64_t>(i) * k + x + lane] = key_score(key);
-          out_ids[static_cast<int64_t>(i) * k + x + lane] = key_id(key);
-        }
-      }
-      if (n_pos < k && lane == 0) {          // fewer than k co-rated neighbours: zero-similarity items by ascending id
-        int filled = n_pos;
-        for (int j = 0; j < n_items && filled < k; ++j) {
-          if (j == i) continue;
-          bool used = false;
-          for (int x = 0; x < n_pos; ++x) used |= (key_id(s0[x]) == j);
-          if (used) continue;
-          out_scores[static_cast<int64_t>(i) * k + filled] = 0.f;
-          out_ids[static_cast<int64_t>(i) * k + filled] = j;
-          ++filled;
-        }
-        for (; filled < k; ++filled) {
-          out_scores[static_cast<int64_t>(i) * k + filled] = -INFINITY;
-          out_ids[static_cast<int64_t>(i) * k + filled] = -1;
-        }
-      }
-    }
-    __syncthreads();
-  }
+// raters per work unit: 2048, raised so that the partial-row buffer (<= nnz / chunk hot items x n_items floats) stays
+// within 1 GiB
+int ii_chunk(int n_items, int64_t nnz) {
+  long long chunk = 2048;
+  const long long budget_rows = (1ll << 30) / (static_cast<long long>(n_items) * 4 + 1);
+  if (budget_rows > 0 && nnz / chunk > budget_rows) chunk = (nnz + budget_rows - 1) / budget_rows;
+  if (chunk < 2048) chunk = 2048;
+  if (chunk > 0x3fffffff) chunk = 0x3fffffff;
+  return static_cast<int>(chunk);
 }
-
-constexpr size_t kGramBudgetBytes = static_cast<size_t>(6) << 30;    // dense path when N*N*4 B <= 6 GiB (N <= ~40k)
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+int ii_max_hot(int n_items, int64_t nnz) {
+  const long long m = nnz / ii_chunk(n_items, nnz) + 1;
+  return static_cast<int>(m < n_items ? m : n_items);
+}
 
 }  // namespace
 
 size_t item_item_workspace_bytes(int64_t n_users, int n_items, int64_t nnz) {
   (void)n_users;
-  const size_t gram = static_cast<size_t>(n_items) * n_items * sizeof(float);
-  if (gram <= kGramBudgetBytes) return align_up(gram, 256) + 256;
   size_t b = 0;
   b += align_up(static_cast<size_t>(n_items + 1) * 8, 256);   // col_cnt
   b += align_up(static_cast<size_t>(n_items + 1) * 8, 256);   // col_ptr
-  b += align_up(static_cast<size_t>(n_items + 1) * 8, 256);   // cursor
+  b += align_up(static_cast<size_t>(n_items + 1) * 8, 256);   // cursor (fallback path)
   b += align_up(static_cast<size_t>(n_items) * 4, 256);       // sq
   b += align_up(static_cast<size_t>(n_items) * 4, 256);       // order
-  b += align_up(static_cast<size_t>(nnz) * 4, 256);           // csc_user
-  b += align_up(static_cast<size_t>(nnz) * 4, 256);           // csc_val
-  b += 1024;                                                  // bucket counters + work counter
+  b += align_up(static_cast<size_t>(n_items + 1) * 4, 256);   // unit_off
+  b += align_up(static_cast<size_t>(n_items) * 4, 256);       // hot_of
+  b += align_up(static_cast<size_t>(nnz) * 8, 256);           // csc (user, rating)
+  b += 1024;                                                  // bucket counters, unit / hot counts, work counter
+  if (n_items <= kSmemHistItems / 2) b += 2 * align_up(static_cast<size_t>(kSortCtas) * n_items * 4, 256);   // per-CTA histograms + square norms
+  const int max_hot = ii_max_hot(n_items, nnz);
+  b += align_up(static_cast<size_t>(max_hot) * n_items * 4, 256);   // partial rows of hot items
+  b += align_up(static_cast<size_t>(max_hot) * 4, 256);             // hot_done
   return b;
 }
 
 cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr, const int32_t* indices,
                              const float* values, int k, float* out_scores, int32_t* out_ids, void* workspace,
                              size_t workspace_bytes, cudaStream_t stream, int* n_launches) {
-  // nnz lives in indptr[n_users] on the device; the caller passes it through workspace_bytes sizing,
-  // so read it back here (one 8-byte copy).
+  // nnz lives in indptr[n_users] on the device (one 8-byte copy)
   int64_t nnz = 0;
   cudaError_t e = cudaMemcpyAsync(&nnz, indptr + n_users, sizeof(int64_t), cudaMemcpyDeviceToHost, stream);
   if (e != cudaSuccess) return e;
   e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) return e;
   if (item_item_workspace_bytes(n_users, n_items, nnz) > workspace_bytes) return cudaErrorInvalidValue;
-  int dev0 = 0, sms0 = 148;
-  cudaGetDevice(&dev0);
-  cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
-  const size_t gram_bytes = static_cast<size_t>(n_items) * n_items * sizeof(float);
-  if (gram_bytes <= kGramBudgetBytes) {
-    float* gram = static_cast<float*>(workspace);
-    e = cudaMemsetAsync(gram, 0, gram_bytes, stream);
-    if (e != cudaSuccess) return e;
-    ii_gram_kernel<<<sms0 * 8, 256, 0, stream>>>(indptr, indices, values, n_users, n_items, gram);
-    ii_select_kernel<<<sms0 * 4, kIIThreads, 0, stream>>>(gram, n_items, k, out_scores, out_ids);
-    if (n_launches != nullptr) *n_launches = 2;
-    return cudaGetLastError();
-  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
   unsigned char* w = static_cast<unsigned char*>(workspace);
   auto take = [&](size_t bytes) { unsigned char* p = w; w += align_up(bytes, 256); return p; };
@@ -364,47 +568,75 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   unsigned long long* cursor = reinterpret_cast<unsigned long long*>(take(static_cast<size_t>(n_items + 1) * 8));
   float* sq = reinterpret_cast<float*>(take(static_cast<size_t>(n_items) * 4));
   int32_t* order = reinterpret_cast<int32_t*>(take(static_cast<size_t>(n_items) * 4));
-  int32_t* csc_user = reinterpret_cast<int32_t*>(take(static_cast<size_t>(nnz) * 4));
-  float* csc_val = reinterpret_cast<float*>(take(static_cast<size_t>(nnz) * 4));
-  int* counters = reinterpret_cast<int*>(take(1024));   // [0..63] bucket_cnt, [64..127] bucket_pos, [128] work counter
+  int* unit_off = reinterpret_cast<int*>(take(static_cast<size_t>(n_items + 1) * 4));
+  int* hot_of = reinterpret_cast<int*>(take(static_cast<size_t>(n_items) * 4));
+  int2* csc = reinterpret_cast<int2*>(take(static_cast<size_t>(nnz) * 8));
+  int* counters = reinterpret_cast<int*>(take(1024));   // [0..63] bucket_cnt, [64..127] bucket_pos, [128] units, [129] hot items, [130] work counter,
+                                                        // [131] integer-accumulator mode, [132] non-integral rating seen, [133] largest rating, [134] flags valid
+  const bool smem_sort = n_items <= kSmemHistItems / 2;   // (count + square-norm histograms side by side)
+  uint32_t* block_hist = smem_sort ? reinterpret_cast<uint32_t*>(take(static_cast<size_t>(kSortCtas) * n_items * 4)) : nullptr;
+  float* block_sq = smem_sort ? reinterpret_cast<float*>(take(static_cast<size_t>(kSortCtas) * n_items * 4)) : nullptr;
+  const int chunk = ii_chunk(n_items, nnz);
+  const int max_hot = ii_max_hot(n_items, nnz);
+  float* hot_rows = reinterpret_cast<float*>(take(static_cast<size_t>(max_hot) * n_items * 4));
+  int* hot_done = reinterpret_cast<int*>(take(static_cast<size_t>(max_hot) * 4));
 
   cudaMemsetAsync(col_cnt, 0, static_cast<size_t>(n_items + 1) * 8, stream);
   cudaMemsetAsync(sq, 0, static_cast<size_t>(n_items) * 4, stream);
   cudaMemsetAsync(counters, 0, 1024, stream);
   int launches = 0;
-  if (nnz > 0) {
-    ii_hist_kernel<<<static_cast<int>((nnz + 255) / 256), 256, 0, stream>>>(indices, values, nnz, col_cnt, sq);
-    ++launches;
+  // ---- 1. CSC
+  if (smem_sort) {
+    const size_t hist_smem = static_cast<size_t>(n_items) * 8;
+    if (hist_smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(ii_block_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hist_smem));
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(ii_block_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hist_smem));
+      if (e != cudaSuccess) return e;
+    }
+    ii_block_hist_kernel<<<kSortCtas, kAccThreads, hist_smem, stream>>>(indptr, indices, values, n_users, nnz, n_items, block_hist, block_sq,
+                                                                       counters + 128 + 4);
+    ii_column_prefix_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(block_hist, block_sq, n_items, col_cnt, sq);
+    ii_scan_kernel<<<1, 1024, 0, stream>>>(col_cnt, n_items, col_ptr, nullptr);
+    ii_block_scatter_kernel<<<kSortCtas, kAccThreads, hist_smem, stream>>>(indptr, indices, values, n_users, nnz, n_items, block_hist,
+                                                                          col_ptr, csc);
+    launches += 4;
+  } else {
+    if (nnz > 0) {
+      ii_hist_kernel<<<static_cast<int>((nnz + 255) / 256), 256, 0, stream>>>(indices, values, nnz, col_cnt, sq);
+      ++launches;
+    }
+    ii_scan_kernel<<<1, 1024, 0, stream>>>(col_cnt, n_items, col_ptr, cursor);
+    ii_sqrt_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(sq, n_items);
+    launches += 2;
+    if (n_users > 0) {
+      ii_scatter_kernel<<<static_cast<int>((n_users * 32 + 255) / 256), 256, 0, stream>>>(indptr, indices, values, n_users,
+                                                                                        cursor, csc);
+      ++launches;
+    }
   }
-  ii_scan_kernel<<<1, 1024, 0, stream>>>(col_cnt, n_items, col_ptr, cursor);
-  ++launches;
-  if (n_users > 0) {
-    ii_scatter_kernel<<<static_cast<int>((n_users * 32 + 255) / 256), 256, 0, stream>>>(indptr, indices, values, n_users,
-                                                                                      cursor, csc_user, csc_val);
-    ++launches;
-  }
+  // ---- 2. work units, hot items first
   ii_bucket_count_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters);
   ii_bucket_scan_kernel<<<1, 32, 0, stream>>>(counters, counters + 64);
   ii_bucket_scatter_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters + 64, order);
-  launches += 3;
+  ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, counters + 128);
+  ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
+  launches += 5;
 
-  // accumulator range: as many items as fit beside the per-warp merge stages
+  // ---- 3. accumulate + select.  Accumulator range: as many items as fit beside the per-warp merge stages
   const int max_smem = 227 * 1024;
-  const int stage_bytes = kIIWarps * kCap * 8;
+  const int stage_bytes = kAccWarps * kCap * 8;
   int range = (max_smem - stage_bytes - 1024) / 4;
   if (range > n_items) range = n_items;
   range = (range + 31) / 32 * 32;
   const size_t smem = static_cast<size_t>(range) * 4 + stage_bytes;
-  e = cudaFuncSetAttribute(ii_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  e = cudaFuncSetAttribute(ii_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
-  int grid = sms * ctas_per_sm;
-  if (grid > n_items) grid = n_items;
-  ii_main_kernel<<<grid, kIIThreads, smem, stream>>>(indptr, indices, values, col_ptr, csc_user, csc_val, sq, order,
-                                                     n_items, range, k, counters + 128, out_scores, out_ids);
+  const int grid = sms * ctas_per_sm;
+  ii_accumulate_kernel<<<grid, kAccThreads, smem, stream>>>(indptr, indices, values, col_ptr, csc, sq, order, unit_off,
+                                                          hot_of, counters + 128, n_items, range, chunk, k, max_hot, hot_rows, hot_done,
+                                                          counters + 130, out_scores, out_ids);
   ++launches;
   if (n_launches != nullptr) *n_launches = launches;
   return cudaGetLastError();

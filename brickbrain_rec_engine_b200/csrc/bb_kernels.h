@@ -53,7 +53,8 @@ cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bi
 // ---- K4 + K6 merge / re-score / emit (bb_aux.cu)
 // comm != nullptr: collective search of a row-sharded catalog -- the k final keys of every query are stored into the
 // owner rank's inbox (peer memory) instead of out_scores / out_ids
-cudaError_t launch_merge_emit(const ScanParams& P, int k, bool rescore, const float* q_f32, const float* cat_f32,
+// rescore: 0 = rank by the scan's scores, n > 0 = re-score the best n candidates in exact fp32
+cudaError_t launch_merge_emit(const ScanParams& P, int k, int rescore, const float* q_f32, const float* cat_f32,
                               bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream);
 cudaError_t launch_merge_inbox(const CommParams& comm, int n_mine, int k, unsigned long long expected, bool as_l2,
                                float* out_scores, int32_t* out_ids, int32_t* err_flag, cudaStream_t stream);

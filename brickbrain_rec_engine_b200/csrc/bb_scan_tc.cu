@@ -537,8 +537,29 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const int64_t sl = static_cast<int64_t>(__ldg(P.self_id + q)) - P.id_offset;
         if (sl >= 0 && sl < P.n_items) self_local = sl;
       }
-      bool excl_only = false;                        // the query's own exclusion lists (rated items) are its only slow predicate
-      if (q_valid && P.q_excl_n > 0) {
+      // The query's own exclusion lists (already-rated items).  ONE list per query (the common case) is walked like
+      // a merge: the warp visits its columns in increasing order, so the lane keeps the next listed id (as a local
+      // row) and a cursor; listed columns are removed from the pass bitmap BEFORE the vote and cost the slow path
+      // nothing.  More than one list per query falls back to a binary search per passing candidate.
+      bool excl_only = false;
+      int ex_next = INT32_MAX, ex_i = 0;             // next listed LOCAL row >= the columns seen so far; its index in the list
+      if (q_valid && P.q_excl_n == 1) {
+        const int32_t l = __ldg(P.q_excl + q);
+        if (l >= 0) {
+          const int64_t lo = __ldg(P.excl_off + l), hi = __ldg(P.excl_off + l + 1);
+          const int64_t first = P.id_offset + static_cast<int64_t>(t0) * kTcTile;
+          int64_t a = lo, b = hi;                    // lower bound of the unit's first row
+          while (a < b) {
+            const int64_t mid = (a + b) >> 1;
+            if (static_cast<int64_t>(__ldg(P.excl_ids + mid)) < first) a = mid + 1; else b = mid;
+          }
+          ex_i = static_cast<int>(a - lo);
+          if (a < hi) {
+            const int64_t r = static_cast<int64_t>(__ldg(P.excl_ids + a)) - P.id_offset;
+            ex_next = r < INT32_MAX ? static_cast<int>(r) : INT32_MAX;
+          }
+        }
+      } else if (q_valid && P.q_excl_n > 1) {
         for (int e = 0; e < P.q_excl_n; ++e) excl_only |= __ldg(P.q_excl + static_cast<int64_t>(q) * P.q_excl_n + e) >= 0;
       }
       const uint32_t* class_row = nullptr;           // this row's constraint-set validity bitmap (class mode)
@@ -637,6 +658,22 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
               else mbar_arrive_local(acc_empty_leader_base + acc * 8);
             }
           }
+          // columns of this chunk that the row's exclusion list names (rare: a cursor compare per chunk)
+          unsigned ex_mask = 0u;
+          {
+            const int64_t c_lo = item0 + chunk * 32;
+            while (static_cast<int64_t>(ex_next) < c_lo + 32) {
+              if (static_cast<int64_t>(ex_next) >= c_lo) ex_mask |= 1u << static_cast<int>(ex_next - c_lo);
+              const int32_t l = __ldg(P.q_excl + q);
+              const int64_t lo = __ldg(P.excl_off + l), hi = __ldg(P.excl_off + l + 1);
+              ++ex_i;
+              ex_next = INT32_MAX;
+              if (lo + ex_i < hi) {
+                const int64_t r = static_cast<int64_t>(__ldg(P.excl_ids + lo + ex_i)) - P.id_offset;
+                if (r < INT32_MAX) ex_next = static_cast<int>(r);
+              }
+            }
+          }
           if (P.dump != nullptr) {
             if (q_valid) {
 #pragma unroll
@@ -650,7 +687,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (P.pilot_mode) {
             // pilot pass: no candidates, only the row's best VALID score of every 8 columns (a group maximum is the score
             // of one distinct valid item, so the m-th largest of them bounds the row's m-th best from below)
-            unsigned vm = class_word & ~__ballot_sync(kFull, col_item >= P.n_items);
+            unsigned vm = class_word & ~ex_mask & ~__ballot_sync(kFull, col_item >= P.n_items);
             const int64_t c0 = item0 + chunk * 32;
             if (self_local >= c0 && self_local < c0 + 32) vm &= ~(1u << static_cast<int>(self_local - c0));
             if (dead) vm = 0u;
@@ -672,7 +709,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           unsigned pm = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) pm |= (__uint_as_float(r[j]) >= thr) ? (1u << j) : 0u;
-          pm &= class_word & ~__ballot_sync(kFull, col_item >= P.n_items);
+          pm &= class_word & ~ex_mask & ~__ballot_sync(kFull, col_item >= P.n_items);
           if (__any_sync(kFull, pm != 0u) && !(P.debug_flags & 1)) {
             // ---- slow path, entered only when some row of this warp has a live candidate
             ++stat_slow;
@@ -748,7 +785,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
         const long long c0 = epi_clock();
         if (P.debug_flags & 3) named_bar_sync(bar_id, kColWarps * 32);
-        const unsigned fresh = __ballot_sync(kFull, !dead && s_cnt[row_in_cta] >= 8);
+        const unsigned fresh = P.skip_unit_end ? 0u : __ballot_sync(kFull, !dead && s_cnt[row_in_cta] >= 8);
         stat_compact += group_compact(P, fresh, (P.debug_flags & 8) ? 0u : kFull, half, s_cnt, s_sorted, s_thr, ew, buf, slot, q, lane);
         named_bar_sync(bar_id, kColWarps * 32);
         cyc_end += epi_clock() - c0;

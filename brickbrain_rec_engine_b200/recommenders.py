@@ -270,9 +270,14 @@ class CollaborativeFilteringRecommender:
         lookup follows the matrix index, and the already-rated lists / the CF universe are rebuilt from the matrix."""
         eng = self.engine
         f = int(self.item_factors.shape[1])
-        if eng.cf_dim < f:
-            raise ValueError(f"engine was created with cf_dim={eng.cf_dim} but the trained model has {f} components: "
-                             "create the engine with cf_dim >= n_components (HybridRecommender.from_arrays(cf_dim=...))")
+        self._engine_mismatch = None
+        if eng.cf_dim < f or self.catalog is None:
+            # the factors were trained but cannot be loaded: scoring must fail loudly instead of using stale operands
+            self._engine_mismatch = (f"engine was created with cf_dim={eng.cf_dim} but the trained model has {f} components: "
+                                     "create the engine with cf_dim >= n_components (HybridRecommender.from_arrays(cf_dim=...))"
+                                     if self.catalog is not None else "no catalog table attached to this recommender")
+            logger.warning("train_svd_model: %s", self._engine_mismatch)
+            return
         n = len(self.catalog)
         # columns of the matrix -> catalog rows (a pivot table names them by set_num, a plain array is positional)
         if hasattr(frame, "columns") and hasattr(frame, "index"):
@@ -307,6 +312,8 @@ class CollaborativeFilteringRecommender:
         if self.svd_model is None:
             logger.info("Using fallback recommendations due to insufficient data")
             return self._cold_start_recommendations(top_k, valid_set_filter)
+        if getattr(self, "_engine_mismatch", None):
+            raise RuntimeError("trained factors are not in the engine: " + self._engine_mismatch)
         if user_id not in self.user_lookup:
             logger.warning("User %s not found in user lookup", user_id)       # :428-430
             return self._cold_start_recommendations(top_k, valid_set_filter)
