@@ -18,5 +18,6 @@ from .vector_store import (BrickVectorStore, Document, apply_document_filters, a
 from .sharded import ShardedSearch, shard_bounds, slice_bounds  # noqa: F401
 from .bulk import BulkSink, bulk_recommend, user_shard  # noqa: F401
 from .cache import RecommendationCache  # noqa: F401
+from .query_producer import DeviceQueryProducer, minilm_shaped_encoder  # noqa: F401
 
 __version__ = "0.1.0"

@@ -570,7 +570,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
       BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
       BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
     }
-    P.pub_cnt = static_cast<int32_t*>(w->pub_cnt.p);
+    P.pub_cnt = small ? nullptr : static_cast<int32_t*>(w->pub_cnt.p);
     P.cand = static_cast<uint64_t*>(w->cand.p);
     P.cand_cnt = static_cast<int32_t*>(w->cand_cnt.p);
     // collective search of a row-sharded catalog: the threshold words live in the exported communication block and

@@ -179,8 +179,19 @@ struct WarpMerger {
   }
   // stage[0..127] is sorted (or empty) and stage[128..] holds <= 128 new keys: sort only the new keys and merge
   // (one compare against the reversed tail + one bitonic merge phase), as in the scan's compaction.
+  // The tail's sort network follows the number of new keys (a query of a sharded search gathers a few dozen).
+  template <int TE>
+  __device__ void sort_tail(uint64_t (&t)[kEpl / 2]) {
+    uint64_t tt[TE];
+#pragma unroll
+    for (int i = 0; i < TE; ++i) tt[i] = t[i];
+    warp_sort_desc<TE>(tt, lane);
+#pragma unroll
+    for (int i = 0; i < kEpl / 2; ++i) t[i] = i < TE ? tt[i < TE ? i : 0] : 0ull;
+  }
   __device__ void flush() {
     constexpr int PE = kEpl / 2;
+    if (n_new == 0) return;                          // (the prefix is sorted already)
     uint64_t p[PE], t[PE];
 #pragma unroll
     for (int i = 0; i < PE; ++i) {
@@ -188,7 +199,9 @@ struct WarpMerger {
       t[i] = stage[kCap / 2 + ((i << 5) | lane)];
     }
     __syncwarp();
-    warp_sort_desc<PE>(t, lane);
+    if (n_new <= 32) sort_tail<1>(t);
+    else if (n_new <= 64) sort_tail<2>(t);
+    else sort_tail<PE>(t);
 #pragma unroll
     for (int i = 0; i < PE; ++i) {
       const uint64_t r = __shfl_sync(kFull, t[PE - 1 - i], 31 - lane);
@@ -234,7 +247,7 @@ struct WarpMerger {
 };
 
 // ------------------------------------------------------------------ K4 + K6: merge, re-score, emit
-// One CTA (4 warps) per query.  Phase 1 (warp 0): gather every split's surviving
+// One CTA (4 warps) per query.  Phase 1 (all warps): gather every split's surviving
 // candidates that are still >= the final shared threshold and keep the best k_sel.
 // Phase 2 (all warps, optional): exact fp32 re-score of the survivors against the
 // fp32 operand copy (gather of k_sel rows of k_pad floats).  Phase 3: final sort, emit.
@@ -248,24 +261,44 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // Phase 1: the four warps gather disjoint quarters of the row's streams (counts are fetched lane-parallel so
-  // the walk is not a chain of dependent L2 round trips), then warp 0 merges the four partial tops.
+  // Phase 1: stream s of the row belongs to warp s % 4.  A warp takes its streams four at a time: the counts were fetched
+  // lane-parallel, the first 32 keys of the four streams are loaded together (the walk is otherwise a chain of dependent
+  // L2 round trips), and -- a unit leaves its buffer as a SORTED, published prefix -- a stream whose first group holds
+  // nothing at or above the final threshold is finished (with ~60 streams per row a couple of keys per stream survive).
   {
     WarpMerger mg;
     mg.init(stage_all[warp], lane);
     const uint32_t thr = thr_load(P, q);
     const int n_slots = P.n_slot_splits * P.n_sub;
-    for (int s0 = warp * 32; s0 < n_slots; s0 += 128) {
-      const int my_s = s0 + lane;
-      const int my_cnt = my_s < n_slots ? __ldcg(P.cand_cnt + static_cast<int64_t>(my_s) * P.b_pad + q) : 0;
-      for (int j = 0; j < 32 && s0 + j < n_slots; ++j) {
-        const int cnt = __shfl_sync(kFull, my_cnt, j);
-        if (cnt == 0) continue;
-        const uint64_t* buf = P.cand + (static_cast<int64_t>(s0 + j) * P.b_pad + q) * P.cap;
-        for (int base = 0; base < cnt; base += 32) {
-          uint64_t key = (base + lane < cnt) ? __ldcg(buf + base + lane) : 0ull;
-          if (static_cast<uint32_t>(key >> 32) < thr) key = 0ull;
-          mg.offer(key);
+    for (int s0 = warp; s0 < n_slots; s0 += 128) {           // lane l of this pass: stream s0 + 4 * l
+      const int my_s = s0 + 4 * lane;
+      const int64_t my_slot = static_cast<int64_t>(my_s) * P.b_pad + q;
+      const int my_cnt = my_s < n_slots ? __ldcg(P.cand_cnt + my_slot) : 0;
+      const int my_sorted = (my_s < n_slots && P.pub_cnt != nullptr) ? __ldcg(P.pub_cnt + my_slot) : 0;
+      const int n_here = min(32, (n_slots - s0 + 3) / 4);
+      for (int j0 = 0; j0 < n_here; j0 += 4) {
+        uint64_t first[4];
+        int cnt[4], sorted[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          cnt[u] = __shfl_sync(kFull, my_cnt, (j0 + u) & 31);
+          sorted[u] = __shfl_sync(kFull, my_sorted, (j0 + u) & 31);
+          if (j0 + u >= n_here) cnt[u] = 0;
+          const uint64_t* buf = P.cand + (static_cast<int64_t>(s0 + 4 * (j0 + u)) * P.b_pad + q) * P.cap;
+          first[u] = lane < cnt[u] ? __ldcg(buf + lane) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (cnt[u] == 0) continue;
+          const uint64_t* buf = P.cand + (static_cast<int64_t>(s0 + 4 * (j0 + u)) * P.b_pad + q) * P.cap;
+          uint64_t key = first[u];
+          for (int base = 0; base < cnt[u]; base += 32) {
+            if (base > 0) key = (base + lane < cnt[u]) ? __ldcg(buf + base + lane) : 0ull;
+            if (static_cast<uint32_t>(key >> 32) < thr) key = 0ull;
+            const bool any = __any_sync(kFull, key != 0ull);
+            mg.offer(key);
+            if (!any && base + 32 <= sorted[u]) base = (sorted[u] > base + 32 ? sorted[u] : base + 32) - 32;   // rest of the sorted prefix: below the threshold
+          }
         }
       }
     }
@@ -273,14 +306,14 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
   }
   __syncthreads();
   // pairwise tree merge of the four sorted partial tops: (0,1) and (2,3) in parallel, then (0,2)
-  if (warp == 0 || warp == 2) {
+  if ((warp == 0 || warp == 2) && stage_all[warp + 1][0] != 0ull) {
     WarpMerger m2;
     m2.stage = stage_all[warp];
     m2.lane = lane;
     m2.absorb_sorted(stage_all[warp + 1]);
   }
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 0 && stage_all[2][0] != 0ull) {
     WarpMerger m2;
     m2.stage = stage_all[0];
     m2.lane = lane;
@@ -293,15 +326,18 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     // because buffers are kept in multiples of 32 and is dropped here.
     for (int c = rescore + threadIdx.x; c < kMaxSel; c += blockDim.x) stage[c] = 0ull;
     __syncthreads();
+    // survivors (sorted, zeros at the end): a shard of a collective search keeps only what beats the GLOBAL bound
+    int n_cand = 0;
+    for (int c = 0; c < rescore; c += 32) n_cand += __popc(__ballot_sync(kFull, c + lane < rescore && stage[c + lane] != 0ull));
     // exact fp32 dot of the query operand with each surviving catalog row.  Eight lanes per candidate, four
     // candidates per warp at a time: every lane keeps up to 14 independent 16-byte gathers in flight, which is what
     // hides the latency of these scattered row reads.
     const float4* qv = reinterpret_cast<const float4*>(q_f32 + static_cast<int64_t>(q) * P.k_pad);
     const int n4 = P.k_pad >> 2;
     const int sub = lane >> 3, l8 = lane & 7;
-    for (int c0 = warp * 4; c0 < rescore; c0 += 16) {
+    for (int c0 = warp * 4; c0 < n_cand; c0 += 16) {
       const int c = c0 + sub;
-      const uint64_t key = c < rescore ? stage[c] : 0ull;
+      const uint64_t key = c < n_cand ? stage[c] : 0ull;
       float acc = 0.f;
       int32_t gid = -1;
       if (key != 0ull) {
@@ -321,13 +357,26 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
     }
     __syncthreads();
     if (warp == 0) {
-      uint64_t v[kEpl / 2];
+      if (n_cand <= 32) {
+        uint64_t v[1] = {stage[lane]};
+        __syncwarp();
+        warp_sort_desc<1>(v, lane);
+        stage[lane] = v[0];
+      } else if (n_cand <= 64) {
+        uint64_t v[2] = {stage[lane], stage[32 + lane]};
+        __syncwarp();
+        warp_sort_desc<2>(v, lane);
+        stage[lane] = v[0];
+        stage[32 + lane] = v[1];
+      } else {
+        uint64_t v[kEpl / 2];
 #pragma unroll
-      for (int i = 0; i < kEpl / 2; ++i) v[i] = stage[(i << 5) | lane];
-      __syncwarp();
-      warp_sort_desc<kEpl / 2>(v, lane);
+        for (int i = 0; i < kEpl / 2; ++i) v[i] = stage[(i << 5) | lane];
+        __syncwarp();
+        warp_sort_desc<kEpl / 2>(v, lane);
 #pragma unroll
-      for (int i = 0; i < kEpl / 2; ++i) stage[(i << 5) | lane] = v[i];
+        for (int i = 0; i < kEpl / 2; ++i) stage[(i << 5) | lane] = v[i];
+      }
     }
     __syncthreads();
   }
@@ -420,15 +469,30 @@ struct WarpMerger32 {
     for (int i = lane; i < 256; i += 32) stage[i] = 0u;
     __syncwarp();
   }
+  // stage[0..127] sorted (or empty), stage[128..] <= 128 new keys: sort the new keys, keep the best 128 of the union
+  // (compare against the reversed tail + one bitonic merge phase)
   __device__ void flush() {
-    uint32_t v[8];
+    if (n_new == 0) return;
+    uint32_t p[4], t[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = stage[(i << 5) | lane];
+    for (int i = 0; i < 4; ++i) {
+      p[i] = stage[(i << 5) | lane];
+      t[i] = stage[128 + ((i << 5) | lane)];
+    }
     __syncwarp();
-    warp_sort_desc<8, uint32_t>(v, lane);
+    warp_sort_desc<4, uint32_t>(t, lane);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) stage[(i << 5) | lane] = (i < 4) ? v[i] : 0u;
-    floor_key = __shfl_sync(kFull, v[3], 31);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t r = __shfl_sync(kFull, t[3 - i], 31 - lane);
+      p[i] = p[i] > r ? p[i] : r;
+    }
+    warp_bitonic_merge_desc<4, uint32_t>(p, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      stage[(i << 5) | lane] = p[i];
+      stage[128 + ((i << 5) | lane)] = 0u;
+    }
+    floor_key = __shfl_sync(kFull, p[3], 31);
     n_new = 0;
     __syncwarp();
   }

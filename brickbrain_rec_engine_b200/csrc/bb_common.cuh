@@ -401,13 +401,14 @@ constexpr int kRefineSlots = 128;
 // best[3] = bound of the row's k'-th best (0 = none).  Collective searches (P.lvl_stride > 0) also derive the rank's
 // LEVEL claims best[l], l = 0..2 ("this rank holds >= k' >> (3 - l) candidates >= best[l]"): if j streams each hold >= r
 // keys >= T the rank holds >= j * r of them, so level m takes the ceil(m / r)-th largest of the streams' r-th best keys.
-__device__ __forceinline__ void warp_refine_threshold(const ScanParams& P, int row, int lane, uint32_t (&best)[4]) {
+template <int kPer>
+__device__ __forceinline__ void warp_refine_threshold_n(const ScanParams& P, int row, int lane, uint32_t (&best)[4]) {
   best[0] = best[1] = best[2] = best[3] = 0u;
   const int n_slots = P.n_slot_splits * P.n_sub;
   if (n_slots <= 1) return;
-  const int stride = (n_slots + kRefineSlots - 1) / kRefineSlots;
+  constexpr int kSlots = kPer * 32;               // streams examined (sort network size)
+  const int stride = (n_slots + kSlots - 1) / kSlots;
   const int n_use = (n_slots + stride - 1) / stride;
-  constexpr int kPer = kRefineSlots / 32;
   int c[kPer];
   int64_t slot[kPer];
   int n_pub = 0;
@@ -448,7 +449,7 @@ __device__ __forceinline__ void warp_refine_threshold(const ScanParams& P, int r
       if (l == 3 && (r < r0 || r >= P.k_sel)) continue;   // (the r = k' level is the stream's own threshold)
       const int m = P.k_sel >> (3 - l);
       const int e = (m + r - 1) / r - 1;              // element e lives in register e>>5 of lane e&31
-      if (e >= kRefineSlots) continue;
+      if (e >= kSlots) continue;
       uint32_t t = 0u;
 #pragma unroll
       for (int i = 0; i < kPer; ++i)
@@ -457,6 +458,14 @@ __device__ __forceinline__ void warp_refine_threshold(const ScanParams& P, int r
       best[l] = t > best[l] ? t : best[l];
     }
   }
+}
+
+// (the sort network follows the number of streams of a row: 23 at the 8-GPU shard size, 60 on one GPU)
+__device__ __forceinline__ void warp_refine_threshold(const ScanParams& P, int row, int lane, uint32_t (&best)[4]) {
+  const int n_slots = P.n_slot_splits * P.n_sub;
+  if (n_slots <= 32) warp_refine_threshold_n<1>(P, row, lane, best);
+  else if (n_slots <= 64) warp_refine_threshold_n<2>(P, row, lane, best);
+  else warp_refine_threshold_n<kRefineSlots / 32>(P, row, lane, best);
 }
 
 // Compacts the buffers of the rows in `need0` (a warp-uniform lane mask; lane l holds row l's RowState): sort /

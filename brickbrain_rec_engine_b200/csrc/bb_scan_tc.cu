@@ -58,10 +58,12 @@ constexpr int kCompactLine = kCapTc - kTcTile;   // a row whose count crosses th
 static_assert(kCompactLine >= kMaxSel, "candidate buffer too small: a compacted row (<= kMaxSel keys) must be below the line");
 static_assert(kTcSubStreams == 1, "one candidate stream per (split, row)");
 constexpr int kColMetaBytes = kEpiWarps * 32 * 16;   // per-warp packed metadata of the 32 columns of a chunk
-constexpr int kRowStateBytes = 3 * 128 * 4 + 64;   // per row: count, sorted prefix, threshold; + compaction flags [3 tiles][4 row groups] + poller word
+constexpr int kRowStateBytes = 3 * 128 * 4 + 128;   // per row: count, sorted prefix, threshold; + compaction flags [3 tiles][4 row groups] + poller word
 constexpr int kThemeBytes = 32 * 128 * 4;         // per-row allowed-theme bitmaps, word-major [32 words][128 rows]
 constexpr long long kWatchdogCycles = 6000000000ll;   // ~3 s: never hang the GPU, trap instead
 constexpr long long kWaveTimeoutCycles = 40000000ll;  // ~20 ms: the grid is not co-resident, give the wave barrier up
+constexpr int kPublishTiles = 64;                     // periodic publication of what a stream learnt (power of two)
+constexpr int kPublishMinNew = 12;                    // ... for rows with at least this many keys since their last compaction
 
 // kRowCons: the batch carries per-row constraint descriptors that are prefiltered in the epilogue (needs the
 // per-row allowed-theme bitmaps in shared memory); otherwise that space is a sixth TMA stage.
@@ -350,6 +352,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   float* s_thr = reinterpret_cast<float*>(s_sorted + 128);                           // [128] row threshold (after compactions)
   unsigned* s_flag = reinterpret_cast<unsigned*>(s_thr + 128);                       // [3][4] rows that crossed the compaction line
   volatile int* s_poll = reinterpret_cast<volatile int*>(s_flag + 12);               // first query row of this CTA's current unit (-2 not yet, -1 done)
+  unsigned* s_pflag = s_flag + 16;                                                   // [3][4] rows picked for a periodic publication
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -765,13 +768,27 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
         if (P.dump == nullptr && !(P.debug_flags & 3) && P.pilot_mode == 0) {
           // ---- tile end: every append of this tile by the row group's four warps is complete and visible
+          // (the periodic mask is taken by ONE warp of the row group before the barrier -- it may miss this tile's last
+          // appends of the other warps, which is harmless -- so that all four warps act on the same rows)
+          if (half == 0) {
+            unsigned pm_rows = 0u;
+            if (((t - t0) & (kPublishTiles - 1)) == kPublishTiles - 1 && t + 8 < t1)
+              pm_rows = __ballot_sync(kFull, !dead && s_cnt[row_in_cta] - s_sorted[row_in_cta] >= kPublishMinNew);
+            if (lane == 0) s_pflag[tslot * 4 + ew] = pm_rows;
+          }
           named_bar_sync(bar_id, kColWarps * 32);
-          const unsigned need = s_flag[tslot * 4 + ew];          // rows that crossed the line in this tile (written before the barrier)
+          unsigned need = s_flag[tslot * 4 + ew];                // rows that crossed the line in this tile (written before the barrier)
           const int pslot = tslot == 0 ? 2 : tslot - 1;
           if (half == 0 && lane == 0) s_flag[pslot * 4 + ew] = 0u;   // recycle the flag word of tile t-1 (next written in tile t+2)
+          // Periodic publication: a stream whose threshold was seeded appends a few dozen keys per unit and never
+          // reaches the compaction line, so what it learnt used to stay private until the unit's end (~0.8 ms, a tenth
+          // of a shard scan on 8 GPUs) while ~18 streams of the row ran elsewhere.  Every kPublishTiles tiles the rows
+          // that gathered enough new keys are compacted, published and refined across streams (and ranks).
+          const unsigned periodic = s_pflag[tslot * 4 + ew];
+          need |= periodic;
           if (need != 0u) {
             const long long c0 = epi_clock();
-            stat_compact += group_compact(P, need, 0u, half, s_cnt, s_sorted, s_thr, ew, buf, slot, q, lane);
+            stat_compact += group_compact(P, need, (P.debug_flags & 16) ? 0u : periodic, half, s_cnt, s_sorted, s_thr, ew, buf, slot, q, lane);
             cyc_compact += epi_clock() - c0;
             named_bar_sync(bar_id, kColWarps * 32);              // new counts / thresholds are visible before the next append
           }

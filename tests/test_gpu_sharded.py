@@ -255,3 +255,33 @@ def test_train_svd_then_score_through_the_engine(bb):
         assert [r.set_num for r in recs] == [cat.set_nums[j] for j in want]
         np.testing.assert_allclose([r.score for r in recs], sc[want], rtol=2e-5, atol=2e-6)
     hyb.engine.close()
+
+
+def test_device_query_producer_keeps_embeddings_on_the_gpu(bb):
+    """SURVEY 8f2: encoder output (a CUDA tensor) goes straight into bb_search; micro-batched queries share one scan;
+    the search_recommendations seam applies the reference's result filters."""
+    import torch
+    n, d = 6000, 384
+    emb = synth.embeddings(n, d, 91, "aniso")
+    themes = synth.themes_table()
+    names = [themes[t] for t in sorted(themes)]
+    docs = [bb.Document(f"set {i}", {"set_num": f"{i:05d}-1", "name": f"set {i}", "year": 2000 + i % 25, "num_parts": 10 + (i * 37) % 3000,
+                                     "theme": names[i % len(names)], "theme_id": i % len(names)}) for i in range(n)]
+    store = bb.BrickVectorStore(emb, docs, precision="fp32")
+    encode = bb.minilm_shaped_encoder("cuda:0")
+    prod = bb.DeviceQueryProducer(encode, store, max_pending=8)
+    texts = [f"space ship with {j} engines and a crew of minifigures" for j in range(5)]
+    s, i = prod.search_tensor(texts, 10)
+    assert s.is_cuda and i.is_cuda and tuple(i.shape) == (5, 10)
+    q_host = encode(texts).cpu().numpy()
+    rs, ri = store.similarity_search_batch(q_host, 10)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=1e-5, atol=2e-6)
+    tickets = [prod.submit(t) for t in texts]
+    got = [prod.result(t, k=10) for t in tickets]
+    assert all(np.array_equal(g[1].cpu().numpy(), ri[j]) for j, g in enumerate(got))
+    pq = {"semantic_query": texts[0], "filters": {"min_pieces": 500}, "confidence": 0.7, "intent": "search"}
+    recs = prod.search_recommendations(pq, top_k=10)
+    want = [int(x) for x in ri[0] if docs[int(x)].metadata["num_parts"] >= 500]
+    assert [int(r["set_num"][:5]) for r in recs] == want and all(r["intent"] == "search" for r in recs)
+    store.engine.close()

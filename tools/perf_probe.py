@@ -35,7 +35,7 @@ def child(n, b, k, cons):
     elif cons in (2, 3):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import bench
-        descs, bitmaps, _ = bench.scenario_descriptors(b)
+        descs, bitmaps, _, _ = bench.scenario_descriptors(b)
         eng.set_theme_sets(bitmaps)
         if cons == 3:
             descs, cidx_np = eng.dedupe_constraints(descs)
