@@ -24,6 +24,7 @@ BB_METRIC_COSINE = 0
 BB_METRIC_IP = 1
 BB_CFG_KEEP_FP32 = 1
 BB_CFG_BUILD_BF16 = 2
+BB_CFG_BUILD_SPLIT = 4
 BB_PREC_FP32 = 0
 BB_PREC_BF16 = 1
 BB_PREC_BF16_RESCORE = 2
@@ -88,7 +89,7 @@ class bb_info(C.Structure):
                 ("last_compactions", C.c_int64), ("mma_wait_epilogue_cycles", C.c_int64),
                 ("mma_wait_tma_cycles", C.c_int64), ("mma_total_cycles", C.c_int64), ("bytes_fp32", C.c_double), ("bytes_bf16", C.c_double),
                 ("scan_ms", C.c_double), ("scan_launches", C.c_int64), ("epilogue_cycles", C.c_int64 * 7), ("round_cycles", C.c_int64 * 16), ("round_wait_cycles", C.c_int64 * 16),
-                ("last_wasted_chunks", C.c_int64)]
+                ("last_wasted_chunks", C.c_int64), ("last_flagged_rows", C.c_int64)]
 
 
 #: every symbol include/brickscore.h declares: name -> (restype, argtypes)

@@ -54,7 +54,10 @@ struct DevBuf {
 
 struct Workspace {
   std::mutex mu;
-  DevBuf q_f32, q_bf16, cand, cand_cnt, pub_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid, pilot;
+  DevBuf q_f32, q_bf16, q_lo, cand, cand_cnt, pub_cnt, thr_g, out_scores, out_ids, misc, stage, dump, shared_valid, pilot, row_flags;
+  alignas(64) CUtensorMap tmap_ql;
+  const void* tmap_ql_ptr = nullptr;
+  int tmap_ql_rows = 0;
   // pinned mirrors: host inputs of a call are packed here and cross PCIe in ONE copy; host outputs come back in one
   unsigned char* h_stage = nullptr;
   size_t h_stage_cap = 0;
@@ -92,6 +95,11 @@ struct bb_handle {
   bool loaded = false;
   float* cat_f32 = nullptr;
   __nv_bfloat16* cat_bf16 = nullptr;
+  __nv_bfloat16* cat_lo = nullptr;        // second bf16 term of the catalog operand (exact-fp32 search on the tensor pipe)
+  unsigned* cat_norm_max = nullptr;       // largest operand-row norm (float bits)
+  alignas(64) CUtensorMap tmap_el;
+  bool tmap_el_ok = false;
+  std::atomic<long long> last_flagged{0};
   int2* meta = nullptr;
   int64_t* excl_off = nullptr;
   int32_t* excl_ids = nullptr;
@@ -288,6 +296,7 @@ int make_tmap(bb_handle* h, CUtensorMap* out, const void* base, uint64_t rows, i
 }
 
 struct Plan {
+  bool split;                                    // exact-fp32 search ran on the tensor pipe (split-bf16 operands)
   int n_qblocks, n_tiles, n_splits, n_groups, b_pad, tile_items, n_units;
   int pilot_tiles, pilot_splits, pilot_groups;   // threshold-seeding pilot pass over the leading tiles (0 = none)
 };
@@ -401,7 +410,12 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
              ScanParams& P, Plan& plan, bool collective) {
   const int B = q->n_queries;
   const int prec = q->precision;
-  const bool tc = prec != BB_PREC_FP32;
+  // Exact fp32 on the tensor pipe: split-bf16 scan + exact re-score + proof of completeness (rows that cannot be proven
+  // fall back to the FFMA scan).  Needs the split catalog plane; small batches keep the HBM-streaming path, collective
+  // searches and score dumps the FFMA tile scan.
+  const bool split = prec == BB_PREC_FP32 && h->cat_lo != nullptr && h->cat_bf16 != nullptr && dump == nullptr && !collective &&
+                     B > kSmallBatch && h->k_pad / 64 <= kTcMaxKBlocks && getenv("BB_FP32_FFMA") == nullptr;
+  const bool tc = prec != BB_PREC_FP32 || split;
   if (tc && h->cat_bf16 == nullptr) return fail(h, BB_ERR_STATE, "bf16 precision requested but BB_CFG_BUILD_BF16 not set");
   if ((!tc || prec == BB_PREC_BF16_RESCORE) && h->cat_f32 == nullptr)
     return fail(h, BB_ERR_STATE, "fp32 operands requested but BB_CFG_KEEP_FP32 not set");
@@ -434,6 +448,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   }
 
   plan = make_plan(h, B, tc);
+  plan.split = split;
   // exact fp32 search of a small batch (the reference's one-query-per-call pattern): stream the catalog once at HBM
   // speed (bb_scan_small.cu) instead of running the 128-row FFMA tile scan on padded rows
   const bool small = !tc && dump == nullptr && B <= kSmallBatch && static_cast<size_t>(kSmallBatch) * h->k_pad * 4 <= 200 * 1024 &&
@@ -517,12 +532,13 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   const size_t qb_bytes = sizeof(__nv_bfloat16) * static_cast<size_t>(plan.b_pad) * KP;
   BB_CUDA(h, w->q_f32.ensure(qf_bytes));
   BB_CUDA(h, w->q_bf16.ensure(qb_bytes));
+  if (split) BB_CUDA(h, w->q_lo.ensure(qb_bytes));
   BB_CUDA(h, launch_prep_queries(static_cast<const float*>(d_emb), static_cast<const int32_t*>(d_item),
                                  static_cast<const float*>(d_cf), static_cast<const float*>(d_wc),
                                  static_cast<const float*>(d_wf), q->w_content_all, q->w_cf_all, B, plan.b_pad, D, F, KP,
                                  (q->flags & BB_Q_EMB_PRENORMALIZED) ? BB_METRIC_IP : h->cfg.metric, h->cat_f32, h->cat_bf16,
                                  h->cfg.id_offset, h->cfg.n_items, static_cast<float*>(w->q_f32.p), w->q_bf16.p,
-                                 w->err_flag(), stream));
+                                 split ? w->q_lo.p : nullptr, w->err_flag(), stream));
   h->launches++;
 
   // ---- candidate state
@@ -562,12 +578,19 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     P.debug_flags = dbg != nullptr ? atoi(dbg) : 0;
   }
   if (dump == nullptr) {
-    const size_t slots = static_cast<size_t>(P.n_slot_splits) * P.n_sub * plan.b_pad;
+    size_t slots = static_cast<size_t>(P.n_slot_splits) * P.n_sub * plan.b_pad;
     P.cap = tc ? kCapTc : kCap;
-    BB_CUDA(h, w->cand.ensure(slots * static_cast<size_t>(P.cap) * sizeof(uint64_t)));
-    BB_CUDA(h, w->cand_cnt.ensure(slots * sizeof(int32_t)));
+    size_t cand_bytes = slots * static_cast<size_t>(P.cap) * sizeof(uint64_t), slots_max = slots;
+    if (split) {                                   // the FFMA fallback pass re-uses the buffers with its own layout
+      const Plan fp = make_plan(h, B, false);
+      const size_t s2 = static_cast<size_t>(fp.n_splits) * fp.b_pad;
+      if (s2 * kCap * sizeof(uint64_t) > cand_bytes) cand_bytes = s2 * kCap * sizeof(uint64_t);
+      if (s2 > slots_max) slots_max = s2;
+    }
+    BB_CUDA(h, w->cand.ensure(cand_bytes));
+    BB_CUDA(h, w->cand_cnt.ensure(slots_max * sizeof(int32_t)));
     if (!small) {
-      BB_CUDA(h, w->pub_cnt.ensure(slots * sizeof(int32_t)));
+      BB_CUDA(h, w->pub_cnt.ensure(slots_max * sizeof(int32_t)));
       BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
     }
     P.pub_cnt = small ? nullptr : static_cast<int32_t*>(w->pub_cnt.p);
@@ -630,7 +653,25 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
       if (rc != BB_OK) return rc;
       h->tmap_e_ok = true;
     }
+    if (split) {
+      if (w->tmap_ql_ptr != w->q_lo.p || w->tmap_ql_rows != plan.b_pad) {
+        int rc = make_tmap(h, &w->tmap_ql, w->q_lo.p, static_cast<uint64_t>(plan.b_pad), KP, kTcRowsPerCta);
+        if (rc != BB_OK) return rc;
+        w->tmap_ql_ptr = w->q_lo.p;
+        w->tmap_ql_rows = plan.b_pad;
+      }
+      if (!h->tmap_el_ok) {
+        std::lock_guard<std::mutex> g(h->mu);
+        if (!h->tmap_el_ok) {
+          int rc = make_tmap(h, &h->tmap_el, h->cat_lo, static_cast<uint64_t>(h->cfg.n_items), KP, kTcTile / h->cta_group);
+          if (rc != BB_OK) return rc;
+          h->tmap_el_ok = true;
+        }
+      }
+    }
   }
+  const void* t_ql = split ? static_cast<const void*>(&w->tmap_ql) : nullptr;
+  const void* t_el = split ? static_cast<const void*>(&h->tmap_el) : nullptr;
 
   // ---- pilot pass + threshold seeds (tcgen05 scan; rows whose validity is a bitmap word: no constraints or class mode)
   const bool pilot = tc && dump == nullptr && plan.pilot_tiles > 0 && (P.cons == nullptr || P.class_valid != nullptr);
@@ -647,7 +688,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     PP.stat_candidates = nullptr;
     PP.wave_counter = w->wave_counter() + 1;
     PP.n_peers = 0;
-    BB_CUDA(h, launch_scan_tc(PP, &w->tmap_q, &h->tmap_e, h->cta_group, plan.pilot_groups, stream));
+    BB_CUDA(h, launch_scan_tc(PP, &w->tmap_q, &h->tmap_e, h->cta_group, plan.pilot_groups, stream, t_ql, t_el));
     const int64_t pilot_items = static_cast<int64_t>(plan.pilot_tiles) * kTcTile;
     BB_CUDA(h, launch_seed_thresholds(PP, pilot_items < h->cfg.n_items ? pilot_items : h->cfg.n_items, stream));
     h->launches += 2;
@@ -667,7 +708,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   }
   if (ev.first != nullptr) BB_CUDA(h, cudaEventRecord(ev.first, stream));
   if (tc) {
-    BB_CUDA(h, launch_scan_tc(P, &w->tmap_q, &h->tmap_e, h->cta_group, plan.n_groups, stream));
+    BB_CUDA(h, launch_scan_tc(P, &w->tmap_q, &h->tmap_e, h->cta_group, plan.n_groups, stream, t_ql, t_el));
   } else if (small) {
     int bt = 1;
     while (bt < B) bt <<= 1;
@@ -685,6 +726,41 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   }
   h->launches++;
   h->last_units = P.n_units;
+  return BB_OK;
+}
+
+// Second half of the exact-fp32 search on the tensor pipe: the merge kernel flagged the rows whose top-k could not be
+// proven complete (ties or near-ties at the boundary of the over-fetch); those rows -- usually none -- are scanned by the
+// FFMA kernel (blocks without a flagged row leave immediately) and merged again over the same outputs.  No host
+// synchronization: both launches are unconditional.
+int run_ffma_rows(bb_handle* h, Workspace* w, const ScanParams& P1, int k, bool as_l2, float* d_scores, int32_t* d_ids,
+                  cudaStream_t stream) {
+  const Plan fp = make_plan(h, P1.n_queries, false);
+  ScanParams P = P1;
+  P.class_valid = nullptr;
+  P.class_words = 0;
+  P.k_sel = (k + 31) / 32 * 32;
+  P.cap = kCap;
+  P.n_sub = 1;
+  P.n_qblocks = fp.n_qblocks;
+  P.n_splits = fp.n_splits;
+  P.n_tiles = fp.n_tiles;
+  P.tile_items = fp.tile_items;
+  P.n_slot_splits = fp.n_splits;
+  P.n_units = fp.n_qblocks * fp.n_splits;
+  P.b_pad = fp.b_pad;
+  P.pilot_mode = 0;
+  P.pilot_max = nullptr;
+  P.skip_unit_end = 0;
+  P.lvl_stride = 0;
+  P.n_peers = 0;
+  P.epoch = ++h->epoch;
+  P.row_active = static_cast<const int32_t*>(w->row_flags.p);
+  const size_t slots = static_cast<size_t>(P.n_slot_splits) * P.b_pad;
+  BB_CUDA(h, cudaMemsetAsync(w->pub_cnt.p, 0, slots * sizeof(int32_t), stream));
+  BB_CUDA(h, launch_scan_fp32(P, static_cast<const float*>(w->q_f32.p), h->cat_f32, stream));
+  BB_CUDA(h, launch_merge_emit(P, k, 0, static_cast<const float*>(w->q_f32.p), h->cat_f32, as_l2, d_scores, d_ids, nullptr, stream));
+  h->launches += 2;
   return BB_OK;
 }
 
@@ -763,6 +839,15 @@ int bb_create(bb_handle** out, const bb_config* cfg) {
     if (h->cfg.flags & BB_CFG_BUILD_BF16) {
       e = cudaMalloc(reinterpret_cast<void**>(&h->cat_bf16), rows * h->k_pad * sizeof(__nv_bfloat16));
       if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "bf16 catalog alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
+    }
+    // split plane: explicit flag, or by default when the catalog is small enough that +2 B per element is nothing
+    const bool want_split = (h->cfg.flags & BB_CFG_BUILD_SPLIT) != 0 ||
+                            (cfg->flags == 0 && rows * h->k_pad * sizeof(__nv_bfloat16) <= (static_cast<size_t>(4) << 30));
+    if (want_split && (h->cfg.flags & BB_CFG_KEEP_FP32) && (h->cfg.flags & BB_CFG_BUILD_BF16)) {
+      e = cudaMalloc(reinterpret_cast<void**>(&h->cat_lo), rows * h->k_pad * sizeof(__nv_bfloat16));
+      if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->cat_norm_max), 256);
+      if (e == cudaSuccess) e = cudaMemset(h->cat_norm_max, 0, 256);
+      if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "split catalog alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
     }
     e = cudaMalloc(reinterpret_cast<void**>(&h->meta), rows * sizeof(int2));
     if (e != cudaSuccess) { fail(nullptr, BB_ERR_NOMEM, "metadata alloc: %s", cudaGetErrorString(e)); return bail(BB_ERR_NOMEM); }
@@ -875,7 +960,7 @@ void bb_destroy(bb_handle* h) {
   for (auto& kv : h->ws) {
     Workspace* w = kv.second;
     for (DevBuf* b : {&w->q_f32, &w->q_bf16, &w->cand, &w->cand_cnt, &w->pub_cnt, &w->thr_g, &w->out_scores, &w->out_ids, &w->misc,
-                      &w->stage, &w->dump, &w->shared_valid})
+                      &w->stage, &w->dump, &w->shared_valid, &w->q_lo, &w->row_flags})
       b->release();
     w->pilot.release();
     if (w->host_flag != nullptr) cudaFreeHost(w->host_flag);
@@ -890,6 +975,8 @@ void bb_destroy(bb_handle* h) {
   if (h->comm) cudaFree(h->comm);
   if (h->cat_f32) cudaFree(h->cat_f32);
   if (h->cat_bf16) cudaFree(h->cat_bf16);
+  if (h->cat_lo) cudaFree(h->cat_lo);
+  if (h->cat_norm_max) cudaFree(h->cat_norm_max);
   if (h->meta) cudaFree(h->meta);
   if (h->excl_off) cudaFree(h->excl_off);
   if (h->excl_ids) cudaFree(h->excl_ids);
@@ -925,6 +1012,11 @@ int bb_get_info(const bb_handle* hc, bb_info* info) {
   info->epilogue_cycles[5] = static_cast<int64_t>(c[14]);
   info->epilogue_cycles[6] = static_cast<int64_t>(c[15]);
   info->last_wasted_chunks = static_cast<int64_t>(c[13]);
+  {
+    int32_t nf = 0;
+    if (h->last_ws != nullptr) BB_CUDA(h, cudaMemcpy(&nf, h->last_ws->ctl + 196, sizeof(nf), cudaMemcpyDeviceToHost));
+    info->last_flagged_rows = nf;
+  }
   {
     unsigned long long r[32] = {0};
     if (h->last_ws != nullptr) BB_CUDA(h, cudaMemcpy(r, h->last_ws->stats() + 32, sizeof(r), cudaMemcpyDeviceToHost));
@@ -1014,7 +1106,8 @@ int bb_load_catalog(bb_handle* h, int64_t row_begin, int64_t n_rows, const float
     const int64_t row = row_begin + r0;
     BB_CUDA(h, launch_prep_catalog(static_cast<const float*>(de), static_cast<const float*>(df), n, D, F, KP,
                                    h->cfg.metric, h->cat_f32 ? h->cat_f32 + row * KP : nullptr,
-                                   h->cat_bf16 ? h->cat_bf16 + row * KP : nullptr, stream));
+                                   h->cat_bf16 ? h->cat_bf16 + row * KP : nullptr, h->cat_lo ? h->cat_lo + row * KP : nullptr,
+                                   h->cat_norm_max, stream));
     if (!factors_only || num_parts != nullptr || year != nullptr || theme_id != nullptr)
       BB_CUDA(h, launch_pack_meta(static_cast<const int32_t*>(dp), static_cast<const int16_t*>(dy),
                                   static_cast<const int16_t*>(dt), n, h->meta + row, stream));
@@ -1191,10 +1284,13 @@ int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_score
   rc = check_deferred_flag(h, w);
   if (rc != BB_OK) return rc;
   const bool rescore = q->precision == BB_PREC_BF16_RESCORE;
-  const int k_sel = k_select(k, rescore);
   const int b_pad = (q->n_queries + 255) / 256 * 256;
   // BB_Q_SHARE_THRESHOLDS: the ranks of a row-sharded catalog prune with each other's bounds; results stay local
   const bool collective = (q->flags & BB_Q_SHARE_THRESHOLDS) != 0 && h->comm_world > 1 && b_pad <= h->comm_rows;
+  // (the exact-fp32 search on the tensor pipe over-fetches like the re-scored bf16 search; run_scan decides with the same test)
+  const bool will_split = q->precision == BB_PREC_FP32 && h->cat_lo != nullptr && h->cat_bf16 != nullptr && !collective &&
+                          q->n_queries > kSmallBatch && h->k_pad / 64 <= kTcMaxKBlocks && getenv("BB_FP32_FFMA") == nullptr;
+  const int k_sel = k_select(k, rescore || will_split);
   ScanParams P;
   Plan plan;
   rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan, collective);
@@ -1203,8 +1299,20 @@ int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_score
   OutPack o;
   rc = out_prepare(h, w, n, out_scores, out_ids, o);
   if (rc != BB_OK) return rc;
+  const bool as_l2 = (q->flags & BB_Q_SCORES_AS_L2) != 0;
+  if (plan.split) {
+    // exact fp32 on the tensor pipe: re-score + proof; flagged rows fall back to the FFMA scan
+    BB_CUDA(h, w->row_flags.ensure(sizeof(int32_t) * static_cast<size_t>(plan.b_pad)));
+    int32_t* n_flagged = reinterpret_cast<int32_t*>(w->ctl + 196);
+    BB_CUDA(h, launch_merge_emit(P, k, k_rescore(k, k_sel), static_cast<const float*>(w->q_f32.p), h->cat_f32, as_l2, o.d_scores, o.d_ids,
+                                 nullptr, stream, static_cast<int32_t*>(w->row_flags.p), n_flagged, h->cat_norm_max));
+    h->launches++;
+    rc = run_ffma_rows(h, w, P, k, as_l2, o.d_scores, o.d_ids, stream);
+    if (rc != BB_OK) return rc;
+    return out_finish(h, w, n, out_scores, out_ids, o, stream);
+  }
   BB_CUDA(h, launch_merge_emit(P, k, rescore ? k_rescore(k, k_sel) : 0, static_cast<const float*>(w->q_f32.p), h->cat_f32,
-                               (q->flags & BB_Q_SCORES_AS_L2) != 0, o.d_scores, o.d_ids, nullptr, stream));
+                               as_l2, o.d_scores, o.d_ids, nullptr, stream));
   h->launches++;
   return out_finish(h, w, n, out_scores, out_ids, o, stream);
 }

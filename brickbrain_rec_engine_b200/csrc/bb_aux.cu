@@ -23,7 +23,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // [e_hat | v | 0-pad] as fp32 and bf16.
 __global__ void __launch_bounds__(256)
 prep_catalog_kernel(const float* __restrict__ emb, const float* __restrict__ cf, int64_t n_rows, int dim, int cf_dim,
-                    int k_pad, int metric, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+                    int k_pad, int metric, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
+                    __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ norm_max) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -39,12 +40,23 @@ prep_catalog_kernel(const float* __restrict__ emb, const float* __restrict__ cf,
     inv_norm_den = (nrm == 0.f) ? 1.f : nrm;
   }
   // emb == nullptr with dim > 0: factor-only reload (re-trained CF factors) -- the embedding columns are kept
+  float ss_op = 0.f;
   for (int c = (emb == nullptr ? dim : 0) + lane; c < k_pad; c += 32) {
     float x = 0.f;
     if (c < dim) x = __fdiv_rn(__ldg(emb + row * dim + c), inv_norm_den);
     else if (c < dim + cf_dim && cf != nullptr) x = __ldg(cf + row * cf_dim + (c - dim));
     if (out_f32 != nullptr) out_f32[row * k_pad + c] = x;
-    if (out_bf16 != nullptr) out_bf16[row * k_pad + c] = __float2bfloat16_rn(x);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    if (out_bf16 != nullptr) out_bf16[row * k_pad + c] = hi;
+    // second bf16 term of the operand split x = hi + lo + r, |r| <= 2^-18 |x| (exact-fp32 search on the tensor pipe)
+    if (out_lo != nullptr) out_lo[row * k_pad + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
+    ss_op = fmaf(x, x, ss_op);
+  }
+  if (norm_max != nullptr) {
+    // largest operand-row norm of the catalog (positive floats order like their bit patterns); with a factor-only reload
+    // the kept embedding part (unit norm or zero) is bounded by 1
+    ss_op = warp_sum(ss_op) + (emb == nullptr && dim > 0 ? 1.f : 0.f);
+    if (lane == 0) atomicMax(norm_max, __float_as_uint(sqrtf(ss_op) * 1.0001f));
   }
 }
 
@@ -56,7 +68,8 @@ prep_queries_kernel(const float* __restrict__ q_emb, const int32_t* __restrict__
                     const float* __restrict__ w_c, const float* __restrict__ w_f, float w_c_all, float w_f_all,
                     int n_queries, int b_pad, int dim, int cf_dim, int k_pad, int metric, const float* __restrict__ cat_f32,
                     const __nv_bfloat16* __restrict__ cat_bf16, int64_t id_offset, int64_t n_items,
-                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int32_t* err_flag) {
+                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_lo,
+                    int32_t* err_flag) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= b_pad) return;
@@ -64,6 +77,7 @@ prep_queries_kernel(const float* __restrict__ q_emb, const int32_t* __restrict__
     for (int c = lane; c < k_pad; c += 32) {
       out_f32[static_cast<int64_t>(row) * k_pad + c] = 0.f;
       out_bf16[static_cast<int64_t>(row) * k_pad + c] = __float2bfloat16_rn(0.f);
+      if (out_lo != nullptr) out_lo[static_cast<int64_t>(row) * k_pad + c] = __float2bfloat16_rn(0.f);
     }
     return;
   }
@@ -101,7 +115,9 @@ prep_queries_kernel(const float* __restrict__ q_emb, const int32_t* __restrict__
       x = __fmul_rn(wf, __ldg(q_cf + static_cast<int64_t>(row) * cf_dim + (c - dim)));
     }
     out_f32[static_cast<int64_t>(row) * k_pad + c] = x;
-    out_bf16[static_cast<int64_t>(row) * k_pad + c] = __float2bfloat16_rn(x);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    out_bf16[static_cast<int64_t>(row) * k_pad + c] = hi;
+    if (out_lo != nullptr) out_lo[static_cast<int64_t>(row) * k_pad + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
   }
 }
 
@@ -251,15 +267,27 @@ struct WarpMerger {
 // candidates that are still >= the final shared threshold and keep the best k_sel.
 // Phase 2 (all warps, optional): exact fp32 re-score of the survivors against the
 // fp32 operand copy (gather of k_sel rows of k_pad floats).  Phase 3: final sort, emit.
+// `verify` (exact-fp32 search on the tensor pipe): the scan ranked by split-bf16 scores (error <= delta, see below) and the
+// best `rescore` candidates were re-scored in exact fp32.  Everything that was NOT re-scored has an approximate score of
+// at most that of the last re-scored candidate, a_bound; if the k-th exact score exceeds a_bound + delta, no outsider can
+// reach the top k and the row is proven exact.  Otherwise the row is flagged for the FFMA scan (row_flags / n_flagged).
+struct VerifyParams {
+  int32_t* row_flags;            // [n_queries] out: 1 = re-scan this row exactly
+  int32_t* n_flagged;
+  const unsigned* cat_norm_max;  // largest operand-row norm of the catalog (float bits)
+  float rel;                     // delta = rel * |query operand| * cat_norm_max
+};
+
 template <bool kScatter>
 __global__ void __launch_bounds__(128)
 merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restrict__ q_f32,
                   const float* __restrict__ cat_f32, int as_l2, float* __restrict__ out_scores,
-                  int32_t* __restrict__ out_ids, const __grid_constant__ CommParams C) {
+                  int32_t* __restrict__ out_ids, const __grid_constant__ CommParams C, const VerifyParams V) {
   __shared__ uint64_t stage_all[4][kCap];
   uint64_t* stage = stage_all[0];
   const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (P.row_active != nullptr && __ldg(P.row_active + q) == 0) return;      // fallback pass: flagged rows only
 
   // Phase 1: stream s of the row belongs to warp s % 4.  A warp takes its streams four at a time: the counts were fetched
   // lane-parallel, the first 32 keys of the four streams are loaded together (the walk is otherwise a chain of dependent
@@ -324,6 +352,8 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
   if (rescore > 0) {
     // `rescore` = number of best candidates (by bf16 score) that are re-scored; the rest of the over-fetch only existed
     // because buffers are kept in multiples of 32 and is dropped here.
+    const uint64_t bound_key = stage[rescore - 1];     // (read by every thread before anything is overwritten)
+    __syncthreads();
     for (int c = rescore + threadIdx.x; c < kMaxSel; c += blockDim.x) stage[c] = 0ull;
     __syncthreads();
     // survivors (sorted, zeros at the end): a shard of a collective search keeps only what beats the GLOBAL bound
@@ -376,6 +406,26 @@ merge_emit_kernel(const ScanParams P, int k, int rescore, const float* __restric
         warp_sort_desc<kEpl / 2>(v, lane);
 #pragma unroll
         for (int i = 0; i < kEpl / 2; ++i) stage[(i << 5) | lane] = v[i];
+      }
+      if (V.row_flags != nullptr) {
+        // proof of completeness (see VerifyParams)
+        float ss = 0.f;
+        for (int i = lane; i < P.k_pad; i += 32) {
+          const float x = __ldg(q_f32 + static_cast<int64_t>(q) * P.k_pad + i);
+          ss = fmaf(x, x, ss);
+        }
+        ss = warp_sum(ss);
+        __syncwarp();
+        if (lane == 0) {
+          bool flagged = false;
+          if (bound_key != 0ull) {
+            const uint64_t kth = stage[k - 1];
+            const float delta = V.rel * sqrtf(ss) * __uint_as_float(__ldg(V.cat_norm_max)) + 1e-30f;
+            flagged = kth == 0ull || !(key_score(kth) > key_score(bound_key) + delta);
+          }
+          V.row_flags[q] = flagged ? 1 : 0;
+          if (flagged) atomicAdd(V.n_flagged, 1);
+        }
       }
     }
     __syncthreads();
@@ -656,22 +706,23 @@ inline int blocks_for(int64_t n, int per_block) { return static_cast<int>((n + p
 }  // namespace
 
 cudaError_t launch_prep_catalog(const float* emb, const float* cf, int64_t n_rows, int dim, int cf_dim, int k_pad,
-                                int metric, float* out_f32, void* out_bf16, cudaStream_t stream) {
+                                int metric, float* out_f32, void* out_bf16, void* out_lo, unsigned* norm_max, cudaStream_t stream) {
   if (n_rows <= 0) return cudaSuccess;
   prep_catalog_kernel<<<blocks_for(n_rows, 8), 256, 0, stream>>>(emb, cf, n_rows, dim, cf_dim, k_pad, metric, out_f32,
-                                                                static_cast<__nv_bfloat16*>(out_bf16));
+                                                                static_cast<__nv_bfloat16*>(out_bf16),
+                                                                static_cast<__nv_bfloat16*>(out_lo), norm_max);
   return cudaGetLastError();
 }
 
 cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const float* q_cf, const float* w_c,
                                 const float* w_f, float w_c_all, float w_f_all, int n_queries, int b_pad, int dim, int cf_dim,
                                 int k_pad, int metric, const float* cat_f32, const void* cat_bf16, int64_t id_offset,
-                                int64_t n_items, float* out_f32, void* out_bf16, int32_t* err_flag,
+                                int64_t n_items, float* out_f32, void* out_bf16, void* out_lo, int32_t* err_flag,
                                 cudaStream_t stream) {
   prep_queries_kernel<<<blocks_for(b_pad, 8), 256, 0, stream>>>(
       q_emb, q_item, q_cf, w_c, w_f, w_c_all, w_f_all, n_queries, b_pad, dim, cf_dim, k_pad, metric, cat_f32,
       static_cast<const __nv_bfloat16*>(cat_bf16), id_offset, n_items, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
-      err_flag);
+      static_cast<__nv_bfloat16*>(out_lo), err_flag);
   return cudaGetLastError();
 }
 
@@ -705,13 +756,19 @@ cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bi
 }
 
 cudaError_t launch_merge_emit(const ScanParams& P, int k, int rescore, const float* q_f32, const float* cat_f32,
-                              bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream) {
+                              bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream,
+                              int32_t* row_flags, int32_t* n_flagged, const unsigned* cat_norm_max) {
+  VerifyParams V{};
+  V.row_flags = row_flags;
+  V.n_flagged = n_flagged;
+  V.cat_norm_max = cat_norm_max;
+  V.rel = 1.0f / 4096.0f;          // 2^-12: operand split (<= 1.2e-5), tensor-pipe and re-score accumulation (K <= 1344 terms)
   if (comm != nullptr) {
-    merge_emit_kernel<true><<<P.n_queries, 128, 0, stream>>>(P, k, rescore, q_f32, cat_f32, 0, nullptr, nullptr, *comm);
+    merge_emit_kernel<true><<<P.n_queries, 128, 0, stream>>>(P, k, rescore, q_f32, cat_f32, 0, nullptr, nullptr, *comm, V);
   } else {
     CommParams none{};
     merge_emit_kernel<false><<<P.n_queries, 128, 0, stream>>>(P, k, rescore, q_f32, cat_f32, as_l2 ? 1 : 0, out_scores,
-                                                              out_ids, none);
+                                                              out_ids, none, V);
   }
   return cudaGetLastError();
 }

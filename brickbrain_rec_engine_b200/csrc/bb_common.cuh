@@ -163,6 +163,9 @@ struct ScanParams {
   int32_t pilot_groups;
   int32_t pilot_mode;                // 1 = this launch is the pilot pass
   int32_t skip_unit_end;             // 1 = units do not sort / publish / refine at their end (no later unit would use it)
+  // exact-fp32 search on the tensor pipe: rows whose tensor-pass result could not be PROVEN complete are re-scanned by the
+  // FFMA kernel; row_active[q] != 0 marks them (nullptr = every row is scanned)
+  const int32_t* row_active;
   // schedule
   int32_t n_qblocks;      // query blocks
   int32_t n_splits;       // catalog splits (units = n_qblocks * n_splits)

@@ -20,16 +20,17 @@ constexpr int kTcRowsPerCta = 128;
 constexpr int kTcMaxKBlocks = 7;  // resident query operand: 7 x 64 bf16 columns
 constexpr int kTcSubStreams = 1;  // candidate streams per (split, row): the four column-slice warps of a row group share one
 // cta_group: 1 or 2.  tmap_q / tmap_e are CUtensorMap objects (host memory, passed by value to the kernel).
+// tmap_ql / tmap_el: tensor maps of the second bf16 terms (query / catalog) -> the exact-fp32 split scan; nullptr = bf16 scan
 cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* tmap_e, int cta_group, int n_groups,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const void* tmap_ql = nullptr, const void* tmap_el = nullptr);
 
 // ---- K2 operand preparation (bb_aux.cu)
 cudaError_t launch_prep_catalog(const float* emb, const float* cf, int64_t n_rows, int dim, int cf_dim, int k_pad,
-                                int metric, float* out_f32, void* out_bf16, cudaStream_t stream);
+                                int metric, float* out_f32, void* out_bf16, void* out_lo, unsigned* norm_max, cudaStream_t stream);
 cudaError_t launch_prep_queries(const float* q_emb, const int32_t* q_item, const float* q_cf, const float* w_c,
                                 const float* w_f, float w_c_all, float w_f_all, int n_queries, int b_pad, int dim, int cf_dim,
                                 int k_pad, int metric, const float* cat_f32, const void* cat_bf16, int64_t id_offset,
-                                int64_t n_items, float* out_f32, void* out_bf16, int32_t* err_flag,
+                                int64_t n_items, float* out_f32, void* out_bf16, void* out_lo, int32_t* err_flag,
                                 cudaStream_t stream);
 cudaError_t launch_pack_meta(const int32_t* num_parts, const int16_t* year, const int16_t* theme, int64_t n_rows,
                              int2* out, cudaStream_t stream);
@@ -55,7 +56,8 @@ cudaError_t launch_mask(const ScanParams& P, int n_constraints, uint32_t* out_bi
 // owner rank's inbox (peer memory) instead of out_scores / out_ids
 // rescore: 0 = rank by the scan's scores, n > 0 = re-score the best n candidates in exact fp32
 cudaError_t launch_merge_emit(const ScanParams& P, int k, int rescore, const float* q_f32, const float* cat_f32,
-                              bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream);
+                              bool as_l2, float* out_scores, int32_t* out_ids, const CommParams* comm, cudaStream_t stream,
+                              int32_t* row_flags = nullptr, int32_t* n_flagged = nullptr, const unsigned* cat_norm_max = nullptr);
 cudaError_t launch_merge_inbox(const CommParams& comm, int n_mine, int k, unsigned long long expected, bool as_l2,
                                float* out_scores, int32_t* out_ids, int32_t* err_flag, cudaStream_t stream);
 // threshold (and level) seeds from the pilot pass's group maxima (P.pilot_max / P.pilot_groups)

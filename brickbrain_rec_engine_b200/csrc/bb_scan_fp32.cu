@@ -58,8 +58,14 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
 
   // row-owner state (warps 0..3 own rows warp*32 + lane)
   const int own_row = static_cast<int>(q_row0) + warp * 32 + lane;
+  // fallback pass of the tensor-pipe exact search: only flagged rows are scanned; a block without one leaves at once
+  bool row_on = warp < 4 && own_row < P.n_queries;
+  if (P.row_active != nullptr) {
+    row_on = row_on && __ldg(P.row_active + own_row) != 0;
+    if (!__syncthreads_or(row_on ? 1 : 0)) return;
+  }
   RowState st;
-  st.thr = (warp < 4 && own_row < P.n_queries) ? -INFINITY : INFINITY;
+  st.thr = row_on ? -INFINITY : INFINITY;
   st.cnt = 0;
   st.sorted = 0;
   st.slot = static_cast<int64_t>(split) * P.n_sub * P.b_pad + (warp < 4 ? own_row : 0);
@@ -123,7 +129,7 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
           for (int c = 0; c < XN; ++c)
             if (item0 + c < P.n_items) P.dump[static_cast<int64_t>(own_row) * P.n_items + item0 + c] = sm.s[r][c];
       } else {
-        if (own_row < P.n_queries) st.thr = fmaxf(st.thr, ord2f(thr_load(P, own_row)));
+        if (row_on) st.thr = fmaxf(st.thr, ord2f(thr_load(P, own_row)));
         for (int g = 0; g < XN / 32; ++g) {
           float4 v[8];
           float m = -INFINITY;
@@ -153,7 +159,7 @@ scan_fp32_kernel(const ScanParams P, const float* __restrict__ Q, const float* _
   }
 
   if (warp < 4 && P.dump == nullptr) {
-    const unsigned fresh = __ballot_sync(kFull, own_row < P.n_queries && st.cnt > 0);
+    const unsigned fresh = __ballot_sync(kFull, row_on && st.cnt > 0);
     warp_compact_if_needed(P, st, own_row, lane, fresh);
     P.cand_cnt[st.slot] = st.cnt;
     if (P.stat_candidates != nullptr && st.cnt > 0) atomicAdd(P.stat_candidates, static_cast<unsigned long long>(st.cnt));

@@ -326,9 +326,15 @@ __device__ __forceinline__ void poll_union_threshold(const ScanParams& P, int ro
   if (best > own3 && best > kOrdNegInf) atomicMax(P.thr_g + row, (static_cast<unsigned long long>(ep) << 32) | best);
 }
 
-template <int CG, bool kRowCons>
+// kSplit: exact-fp32 search on the tensor pipe.  Operands are split into two bf16 terms, x = hi + lo + r with
+// |r| <= 2^-18 |x|, and a tile accumulates q_hi.e_hi + q_lo.e_hi + q_hi.e_lo in fp32 (the dropped terms are below
+// 1.2e-5 |q||e|).  q_hi stays resident like the bf16 operand; per k-block the ring carries THREE slots -- e_hi, q_lo,
+// e_lo -- so a tile streams 3x the bytes for 3x the MMAs (same bytes per MMA as the bf16 scan).  The epilogue is
+// unchanged; the merge kernel re-scores the survivors in exact fp32 and PROVES the top-k complete or flags the row.
+template <int CG, bool kRowCons, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
+               const __grid_constant__ CUtensorMap tmap_ql, const __grid_constant__ CUtensorMap tmap_el,
                const ScanParams P, const int n_groups) {
   using C = Cfg<CG, kRowCons>;
   extern __shared__ unsigned char smem_raw[];
@@ -379,6 +385,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_e);
+    if constexpr (kSplit) {
+      prefetch_tmap(&tmap_ql);
+      prefetch_tmap(&tmap_el);
+    }
   }
   if (warp == 2) tmem_alloc<CG>(smem_u32(tmem_slot), kTmemCols);
   tc_fence_before();
@@ -421,11 +431,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         for (int t = t0; t < t1; ++t) {
           const int item0 = t * kTcTile + static_cast<int>(cta_rank) * C::kBRows;
           for (int kb = 0; kb < n_kb; ++kb) {
-            mbar_wait(smem_u32(bar_empty + stage), phase ^ 1, err, 102);
-            const uint32_t full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_full + stage), 0) : smem_u32(bar_full + stage);
-            if (leader) mbar_arrive_expect_tx(smem_u32(bar_full + stage), static_cast<uint32_t>(CG * C::kBStageBytes));
-            tma_load_2d<CG>(&tmap_e, full_leader, smem_u32(smem_b + stage * C::kBStageBytes), kb * kBlockK, item0);
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            // slots of a k-block: e_hi [, q_lo, e_lo]
+#pragma unroll
+            for (int part = 0; part < (kSplit ? 3 : 1); ++part) {
+              mbar_wait(smem_u32(bar_empty + stage), phase ^ 1, err, 102);
+              const uint32_t full_leader = (CG == 2) ? mapa_u32(smem_u32(bar_full + stage), 0) : smem_u32(bar_full + stage);
+              const uint32_t dst = smem_u32(smem_b + stage * C::kBStageBytes);
+              if (part == 1) {
+                if (leader) mbar_arrive_expect_tx(smem_u32(bar_full + stage), static_cast<uint32_t>(CG * kAkbBytes));
+                tma_load_2d<CG>(&tmap_ql, full_leader, dst, kb * kBlockK, row0);
+              } else {
+                if (leader) mbar_arrive_expect_tx(smem_u32(bar_full + stage), static_cast<uint32_t>(CG * C::kBStageBytes));
+                tma_load_2d<CG>(part == 0 ? &tmap_e : &tmap_el, full_leader, dst, kb * kBlockK, item0);
+              }
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            }
           }
         }
         if (P.wave_counter != nullptr) atomicAdd(P.wave_counter, 1u);
@@ -453,23 +473,53 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kAccCols;
           for (int kb = 0; kb < n_kb; ++kb) {
-            tw = clock64();
-            mbar_wait(smem_u32(bar_full + stage), phase, err, 105);
-            t_full_wait += clock64() - tw;
-            tc_fence_after();
-            if (lane == 0) {
-              const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + kb * kAkbBytes));
-              const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * C::kBStageBytes));
+            if constexpr (!kSplit) {
+              tw = clock64();
+              mbar_wait(smem_u32(bar_full + stage), phase, err, 105);
+              t_full_wait += clock64() - tw;
+              tc_fence_after();
+              if (lane == 0) {
+                const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + kb * kAkbBytes));
+                const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + stage * C::kBStageBytes));
 #pragma unroll
-              for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
-                // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
-                umma_bf16<CG>(d_tmem, a_desc + static_cast<uint64_t>(ks * 2), b_desc + static_cast<uint64_t>(ks * 2), idesc,
-                              static_cast<uint32_t>((kb | ks) != 0));
+                for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
+                  // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (>>4) start-address field
+                  umma_bf16<CG>(d_tmem, a_desc + static_cast<uint64_t>(ks * 2), b_desc + static_cast<uint64_t>(ks * 2), idesc,
+                                static_cast<uint32_t>((kb | ks) != 0));
+                }
+                umma_commit<CG>(smem_u32(bar_empty + stage));      // stage reusable once these MMAs retire
               }
-              umma_commit<CG>(smem_u32(bar_empty + stage));      // stage reusable once these MMAs retire
+              __syncwarp();
+              if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            } else {
+              // q_hi.e_hi, q_lo.e_hi (the e_hi slot serves both), q_hi.e_lo
+              uint32_t slot[3];
+#pragma unroll
+              for (int part = 0; part < 3; ++part) {
+                tw = clock64();
+                mbar_wait(smem_u32(bar_full + stage), phase, err, 105);
+                t_full_wait += clock64() - tw;
+                tc_fence_after();
+                slot[part] = stage;
+                if (lane == 0) {
+                  const uint64_t a_desc = make_smem_desc(part == 1 ? smem_u32(smem_b + slot[1] * C::kBStageBytes)
+                                                                   : smem_u32(smem_a + kb * kAkbBytes));
+                  const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + slot[part == 2 ? 2 : 0] * C::kBStageBytes));
+#pragma unroll
+                  for (int ks = 0; ks < kBlockK / kUmmaK; ++ks)
+                    umma_bf16<CG>(d_tmem, a_desc + static_cast<uint64_t>(ks * 2), b_desc + static_cast<uint64_t>(ks * 2), idesc,
+                                  static_cast<uint32_t>((kb | ks | part) != 0));
+                  if (part == 1) {                                   // e_hi and q_lo are free once both products retired
+                    umma_commit<CG>(smem_u32(bar_empty + slot[0]));
+                    umma_commit<CG>(smem_u32(bar_empty + slot[1]));
+                  } else if (part == 2) {
+                    umma_commit<CG>(smem_u32(bar_empty + slot[2]));
+                  }
+                }
+                __syncwarp();
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+              }
             }
-            __syncwarp();
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
           if (lane == 0) umma_commit<CG>(smem_u32(bar_acc_full + acc));   // accumulator ready
           __syncwarp();
@@ -843,9 +893,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 }  // namespace
 
 cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* tmap_e, int cta_group, int n_groups,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const void* tmap_ql, const void* tmap_el) {
   const CUtensorMap* tq = static_cast<const CUtensorMap*>(tmap_q);
   const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e);
+  const bool split = tmap_ql != nullptr && tmap_el != nullptr;
+  const CUtensorMap* tql = split ? static_cast<const CUtensorMap*>(tmap_ql) : tq;
+  const CUtensorMap* tel = split ? static_cast<const CUtensorMap*>(tmap_el) : te;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kThreads);
@@ -862,14 +915,18 @@ cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, *tq, *te, P, n_groups);
+    return cudaLaunchKernelEx(&cfg, kernel, *tq, *te, *tql, *tel, P, n_groups);
   };
   if (cta_group == 2) {
-    return row_cons ? launch(scan_tc_kernel<2, true>, Cfg<2, true>::kSmemBytes, 2)
-                    : launch(scan_tc_kernel<2, false>, Cfg<2, false>::kSmemBytes, 2);
+    if (split) return row_cons ? launch(scan_tc_kernel<2, true, true>, Cfg<2, true>::kSmemBytes, 2)
+                               : launch(scan_tc_kernel<2, false, true>, Cfg<2, false>::kSmemBytes, 2);
+    return row_cons ? launch(scan_tc_kernel<2, true, false>, Cfg<2, true>::kSmemBytes, 2)
+                    : launch(scan_tc_kernel<2, false, false>, Cfg<2, false>::kSmemBytes, 2);
   }
-  return row_cons ? launch(scan_tc_kernel<1, true>, Cfg<1, true>::kSmemBytes, 1)
-                  : launch(scan_tc_kernel<1, false>, Cfg<1, false>::kSmemBytes, 1);
+  if (split) return row_cons ? launch(scan_tc_kernel<1, true, true>, Cfg<1, true>::kSmemBytes, 1)
+                             : launch(scan_tc_kernel<1, false, true>, Cfg<1, false>::kSmemBytes, 1);
+  return row_cons ? launch(scan_tc_kernel<1, true, false>, Cfg<1, true>::kSmemBytes, 1)
+                  : launch(scan_tc_kernel<1, false, false>, Cfg<1, false>::kSmemBytes, 1);
 }
 
 }  // namespace bb

@@ -66,7 +66,9 @@ class ScoringEngine:
 
     def __init__(self, n_items: int, dim: int, cf_dim: int = 0, device: int = 0, id_offset: int = 0,
                  k_max: int = 128, max_batch: int = 0, metric: str = "cosine", keep_fp32: bool = True,
-                 build_bf16: bool = True, theme_bits: int = 1024):
+                 build_bf16: bool = True, theme_bits: int = 1024, build_split: Optional[bool] = None):
+        """``build_split``: the second bf16 term of the operands, which puts ``precision="fp32"`` searches on the tensor
+        pipe (None = the library's default: built when it costs at most 4 GiB)."""
         self._lib = L.load()
         cfg = L.bb_config()
         cfg.struct_size = C.sizeof(L.bb_config)
@@ -80,6 +82,10 @@ class ScoringEngine:
         cfg.theme_bits = theme_bits
         cfg.metric = L.METRICS[metric]
         cfg.flags = (L.BB_CFG_KEEP_FP32 if keep_fp32 else 0) | (L.BB_CFG_BUILD_BF16 if build_bf16 else 0)
+        if build_split is None:
+            build_split = keep_fp32 and build_bf16 and n_items * ((dim + cf_dim + 63) // 64 * 64) * 2 <= (4 << 30)
+        if build_split:
+            cfg.flags |= L.BB_CFG_BUILD_SPLIT
         h = C.c_void_p()
         rc = self._lib.bb_create(C.byref(h), C.byref(cfg))
         if rc != L.BB_OK:

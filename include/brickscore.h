@@ -51,9 +51,14 @@ extern "C" {
 /* bb_config.flags */
 #define BB_CFG_KEEP_FP32 1u  /* keep the fp32 operand copy (exact path, re-scoring) */
 #define BB_CFG_BUILD_BF16 2u /* build the bf16 operand copy (tcgen05 path) */
+#define BB_CFG_BUILD_SPLIT 4u /* build the second bf16 term of the operands (+2 B per element): BB_PREC_FP32 searches then run on
+                                 the tensor pipe (split-bf16 scan, exact re-score, proof of completeness, FFMA fallback per row).
+                                 Default (flags = 0): built when the plane is <= 4 GiB */
 
 /* bb_query_batch.precision */
-#define BB_PREC_FP32 0         /* exact fp32 scan (FFMA), the parity path */
+#define BB_PREC_FP32 0         /* exact fp32 search, the parity path: ids and scores of an fp32 evaluation.  With the split plane:
+                                  tensor-pipe scan + exact re-score + per-row proof (flagged rows are re-scanned with FFMAs);
+                                  without it, or for collective searches: FFMA scan; <= 16 queries: one HBM pass */
 #define BB_PREC_BF16 1         /* tcgen05 bf16 scan, fp32 accumulate, ranks by bf16 scores */
 #define BB_PREC_BF16_RESCORE 2 /* tcgen05 bf16 scan over-fetches, survivors re-scored in exact fp32 */
 
@@ -154,6 +159,7 @@ typedef struct bb_info {
   int64_t round_cycles[16];
   int64_t round_wait_cycles[16];
   int64_t last_wasted_chunks; /* slow-path chunks whose passing scores were all masked out (no append) */
+  int64_t last_flagged_rows;  /* exact-fp32 search on the tensor pipe: rows of the last search that fell back to the FFMA scan */
 } bb_info;
 
 BB_API const char* bb_version(void);

@@ -35,6 +35,17 @@ def _mix_valid(cons_idx, parts, year):
     return np.stack([v[c] for c in cons_idx])
 
 
+def _same_exact_ranking(ref_i, ref_s, got_i, got_s, what):
+    """Two exact-fp32 paths (tensor pipe + re-score vs FFMA tile scan) sum in different orders.  Position by position the
+    scores must agree to fp32 rounding -- a missed or wrong item would show up as a lower score -- and ids may differ only
+    where that happens between items whose scores tie within the rounding (a handful per thousand)."""
+    ref_i, got_i = np.asarray(ref_i), np.asarray(got_i)
+    assert ref_i.shape == got_i.shape, what
+    np.testing.assert_allclose(np.asarray(got_s, np.float64), np.asarray(ref_s, np.float64), rtol=1e-5, atol=2e-6, err_msg=what)
+    assert ((ref_i >= 0) == (got_i >= 0)).all(), what
+    assert (ref_i != got_i).mean() < 0.01, (what, float((ref_i != got_i).mean()))
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16_rescore"])
 def test_per_call_allow_bitmaps_and_query_exclusions(bb, precision):
     """The request's valid_set_filter travels with the call (bb_query_batch.allow_bitmaps) and the users' rated
@@ -160,7 +171,9 @@ def test_collective_search_shards_on_one_gpu(bb, world):
                 assert mine[r] == hi - lo
                 s, i = got[r]
                 if prec == "fp32":
-                    assert np.array_equal(i, fi[lo:hi]) and np.array_equal(s, fs[lo:hi]), (prec, r)
+                    # ids bit-identical; scores to fp32 rounding (the single engine's exact search runs on the tensor
+                    # pipe and re-scores with another summation order than the shards' FFMA scan)
+                    _same_exact_ranking(fi[lo:hi], fs[lo:hi], i, s, f"fp32 shard {r}")
                 else:
                     rec = np.mean([len(set(i[x]) & set(fi[lo + x])) / k for x in range(hi - lo)])
                     assert rec >= 0.999, (prec, r, rec)
@@ -285,3 +298,41 @@ def test_device_query_producer_keeps_embeddings_on_the_gpu(bb):
     want = [int(x) for x in ri[0] if docs[int(x)].metadata["num_parts"] >= 500]
     assert [int(r["set_num"][:5]) for r in recs] == want and all(r["intent"] == "search" for r in recs)
     store.engine.close()
+
+
+@pytest.mark.parametrize("k", [10, 100])
+def test_exact_fp32_on_the_tensor_pipe_equals_the_ffma_scan(bb, k):
+    """BB_PREC_FP32 with the split plane runs on tcgen05 (split-bf16 operands), re-scores in exact fp32 and proves each
+    row's top-k complete; rows it cannot prove (ties at the over-fetch boundary) fall back to the FFMA scan.  The result
+    must equal the FFMA path on (a) tie-free data -- where almost no row may need the fallback -- and (b) a catalog
+    made of 64 copies of each row, where the fallback carries most rows."""
+    n, d, f, b = 61440, 384, 64, 300
+    themes, emb, itf, parts, year, theme = _catalog(n, d, f, 131)
+    rng = np.random.default_rng(2)
+    q = synth.embeddings(b, d, 132, "aniso") * 1.3
+    u = synth.cf_factors(b, f, 133)
+    self_id = rng.integers(0, n, b).astype(np.int32)
+    rated = [np.sort(rng.choice(n, 30, replace=False)).astype(np.int32) for _ in range(b)]
+    cons = _mix_constraints(bb, 4)
+    cidx = (np.arange(b) % 4).astype(np.int32)
+    # (b): every catalog row exists 64 times -> every score is a 64-way exact tie, the boundary of any over-fetch cuts a tie group
+    dup = n // 64
+    for label, e_mat, f_mat in (("tie-free", emb, itf), ("64-way ties", np.tile(emb[:dup], (64, 1))[:n], np.tile(itf[:dup], (64, 1))[:n])):
+        eng = bb.ScoringEngine(n, d, f)
+        eng.load_catalog(emb=np.ascontiguousarray(e_mat), item_factors=np.ascontiguousarray(f_mat), num_parts=parts, year=year, theme_id=theme)
+        eng.set_exclusion_lists(rated)
+        kw = dict(q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6,
+                  constraints=cons, constraint_index=cidx, self_id=self_id, excl_lists=np.arange(b, dtype=np.int32), precision="fp32")
+        s_t, i_t = eng.search(k, **kw)
+        flagged = eng.info()["last_flagged_rows"]
+        os.environ["BB_FP32_FFMA"] = "1"
+        try:
+            s_f, i_f = eng.search(k, **kw)
+        finally:
+            os.environ.pop("BB_FP32_FFMA", None)
+        _same_exact_ranking(i_f, s_f, i_t, s_t, f"{label} k={k} flagged={flagged}")
+        if label == "tie-free":
+            assert flagged <= b // 20, (label, flagged)
+        else:
+            assert flagged >= 10, ("tied data must exercise the fallback", flagged)
+        eng.close()

@@ -69,7 +69,15 @@ def main():
     def same(prec, s, i, fs, fi, ref_i, ref_s):
         s, i = (x.cpu().numpy() if torch.is_tensor(x) else x for x in (s, i))
         if prec == "fp32":
-            return np.array_equal(i, fi) and np.array_equal(s, fs)
+            # two exact paths (tensor pipe + re-score on the single engine, FFMA scan on the shards) sum in different
+            # orders: scores equal to fp32 rounding, ids identical except where two neighbours tie within that rounding
+            if not np.allclose(s, fs, rtol=1e-5, atol=2e-6):
+                return False
+            diff = i != fi
+            if not diff.any():
+                return True
+            gap_ok = np.abs(np.where(diff, s - fs, 0.0)) <= 4e-6 * np.maximum(1.0, np.abs(fs))
+            return bool(gap_ok.all() and diff.mean() < 0.005)
         rec = np.mean([len(set(i[r]) & set(ref_i[r])) / k for r in range(i.shape[0])]) if i.shape[0] else 1.0
         m = i == ref_i
         return rec >= 0.999 and np.allclose(s[m], ref_s[m], rtol=1e-5, atol=2e-6)
