@@ -179,9 +179,9 @@ cudaError_t launch_score_b(const float* q_f32, const float* cat_f32, int64_t n_i
 }  // namespace
 
 int small_scan_splits(int64_t n_items) {
-  int64_t s = (n_items + 4095) / 4096;          // the selection is a latency-bound single-CTA loop: keep it short
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
+  int64_t s = (n_items + 1023) / 1024;          // the selection is a latency-bound single-CTA loop: keep it short (one
+  if (s < 1) s = 1;                             // pass of 8 loads per thread at catalog size)
+  if (s > 128) s = 128;
   return static_cast<int>(s);
 }
 
