@@ -16,8 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libbrickscore.so")
-SOURCES = ["bb_api.cu", "bb_aux.cu", "bb_scan_fp32.cu", "bb_scan_tc.cu", "bb_itemitem.cu", "bb_spmm.cu", "bb_scan_small.cu"]
-HEADERS = ["bb_common.cuh", "bb_kernels.h", os.path.join("..", "..", "include", "brickscore.h")]
+# (the tcgen05 scan is one template in bb_scan_tc.cuh; its variants are separate translation units so they compile in parallel)
+SOURCES = ["bb_scan_tc_bf16.cu", "bb_scan_tc_split.cu", "bb_scan_tc_pilot.cu", "bb_scan_tc_cg1.cu", "bb_api.cu", "bb_aux.cu", "bb_scan_fp32.cu",
+           "bb_itemitem.cu", "bb_spmm.cu", "bb_scan_small.cu"]
+HEADERS = ["bb_common.cuh", "bb_kernels.h", "bb_scan_tc.cuh", os.path.join("..", "..", "include", "brickscore.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

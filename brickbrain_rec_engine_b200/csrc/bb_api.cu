@@ -358,7 +358,7 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   // times: on a 25k-row catalog that was 90% of the scan).  The pilot tiles are scanned twice; keep them <= 1/4 of the
   // catalog and <= 8192 rows (1024 group maxima per row).
   p.pilot_tiles = p.pilot_splits = p.pilot_groups = 0;
-  if (tc && p.n_tiles >= 32 && getenv("BB_NO_PILOT") == nullptr) {
+  if (tc && p.n_tiles >= 32 && h->cta_group == 2 && getenv("BB_NO_PILOT") == nullptr) {
     int pt = p.n_tiles / 4;
     if (pt > 8192 / p.tile_items) pt = 8192 / p.tile_items;
     int ps = hw_groups / p.n_qblocks;
@@ -413,7 +413,7 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   // Exact fp32 on the tensor pipe: split-bf16 scan + exact re-score + proof of completeness (rows that cannot be proven
   // fall back to the FFMA scan).  Needs the split catalog plane; small batches keep the HBM-streaming path, collective
   // searches and score dumps the FFMA tile scan.
-  const bool split = prec == BB_PREC_FP32 && h->cat_lo != nullptr && h->cat_bf16 != nullptr && dump == nullptr && !collective &&
+  const bool split = prec == BB_PREC_FP32 && h->cat_lo != nullptr && h->cat_bf16 != nullptr && dump == nullptr && !collective && h->cta_group == 2 &&
                      B > kSmallBatch && h->k_pad / 64 <= kTcMaxKBlocks && getenv("BB_FP32_FFMA") == nullptr;
   const bool tc = prec != BB_PREC_FP32 || split;
   if (tc && h->cat_bf16 == nullptr) return fail(h, BB_ERR_STATE, "bf16 precision requested but BB_CFG_BUILD_BF16 not set");
@@ -1288,7 +1288,7 @@ int bb_search(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_score
   // BB_Q_SHARE_THRESHOLDS: the ranks of a row-sharded catalog prune with each other's bounds; results stay local
   const bool collective = (q->flags & BB_Q_SHARE_THRESHOLDS) != 0 && h->comm_world > 1 && b_pad <= h->comm_rows;
   // (the exact-fp32 search on the tensor pipe over-fetches like the re-scored bf16 search; run_scan decides with the same test)
-  const bool will_split = q->precision == BB_PREC_FP32 && h->cat_lo != nullptr && h->cat_bf16 != nullptr && !collective &&
+  const bool will_split = q->precision == BB_PREC_FP32 && h->cat_lo != nullptr && h->cat_bf16 != nullptr && !collective && h->cta_group == 2 &&
                           q->n_queries > kSmallBatch && h->k_pad / 64 <= kTcMaxKBlocks && getenv("BB_FP32_FFMA") == nullptr;
   const int k_sel = k_select(k, rescore || will_split);
   ScanParams P;

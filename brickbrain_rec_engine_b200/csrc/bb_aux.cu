@@ -164,18 +164,32 @@ mask_kernel(const ScanParams P, int c_begin, int n_cons, uint32_t* __restrict__ 
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   unsigned long long count = 0;                  // lane c: valid items of constraint c seen by this warp
-  for (int64_t w = warp0; w < n_words; w += n_warps) {
-    const int64_t item = (w << 5) + lane;
-    const bool in = item < P.n_items;
-    const int2 m = in ? __ldg(P.meta + item) : make_int2(0, 0);
-    unsigned mine = 0u;
+  constexpr int U = 4;                           // bitmap words per warp step: four independent 256-byte metadata reads in flight
+  for (int64_t w0 = warp0 * U; w0 < n_words; w0 += n_warps * U) {
+    int2 m[U];
+    bool in[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t item = ((w0 + u) << 5) + lane;
+      in[u] = item < P.n_items;
+      m[u] = in[u] ? __ldg(P.meta + item) : make_int2(0, 0);
+    }
+    unsigned mine[U] = {0u, 0u, 0u, 0u};
     for (int c = 0; c < n_cons; ++c) {
-      const unsigned bits = __ballot_sync(kFull, in && constraint_ok_meta(P, s_cons[c], item, m));
-      if (lane == c) mine = bits;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned bits = __ballot_sync(kFull, in[u] && constraint_ok_meta(P, s_cons[c], ((w0 + u) << 5) + lane, m[u]));
+        if (lane == c) mine[u] = bits;
+      }
     }
     if (lane < n_cons) {
-      out_bitmaps[static_cast<int64_t>(c_begin + lane) * n_words + w] = mine;
-      count += __popc(mine);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (w0 + u < n_words) {
+          out_bitmaps[static_cast<int64_t>(c_begin + lane) * n_words + w0 + u] = mine[u];
+          count += __popc(mine[u]);
+        }
+      }
     }
   }
   if (lane < n_cons && count) atomicAdd(out_counts + c_begin + lane, count);

@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#pragma once
 #include "bb_common.cuh"
 #include "bb_kernels.h"
 
@@ -331,7 +332,9 @@ __device__ __forceinline__ void poll_union_threshold(const ScanParams& P, int ro
 // 1.2e-5 |q||e|).  q_hi stays resident like the bf16 operand; per k-block the ring carries THREE slots -- e_hi, q_lo,
 // e_lo -- so a tile streams 3x the bytes for 3x the MMAs (same bytes per MMA as the bf16 scan).  The epilogue is
 // unchanged; the merge kernel re-scores the survivors in exact fp32 and PROVES the top-k complete or flags the row.
-template <int CG, bool kRowCons, bool kSplit>
+// kPilot: the threshold-seeding pass (group maxima instead of candidates); a separate instantiation keeps its code and
+// registers out of the main scan.
+template <int CG, bool kRowCons, bool kSplit, bool kPilot>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_e,
                const __grid_constant__ CUtensorMap tmap_ql, const __grid_constant__ CUtensorMap tmap_el,
@@ -543,7 +546,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     }
   } else if (warp == 3) {
     // ============================== union-threshold poller (collective searches) ==============================
-    if (P.n_peers > 0 && P.lvl_stride > 0 && P.pilot_mode == 0 && P.dump == nullptr) {
+    if (!kPilot && P.n_peers > 0 && P.lvl_stride > 0 && P.dump == nullptr) {
       while (true) {
         const int base = *s_poll;
         if (base == -1) break;
@@ -737,7 +740,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             continue;
           }
-          if (P.pilot_mode) {
+          if constexpr (kPilot) {
             // pilot pass: no candidates, only the row's best VALID score of every 8 columns (a group maximum is the score
             // of one distinct valid item, so the m-th largest of them bounds the row's m-th best from below)
             unsigned vm = class_word & ~ex_mask & ~__ballot_sync(kFull, col_item >= P.n_items);
@@ -816,7 +819,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             cyc_slow += epi_clock() - c0;
           }
         }
-        if (P.dump == nullptr && !(P.debug_flags & 3) && P.pilot_mode == 0) {
+        if (!kPilot && P.dump == nullptr && !(P.debug_flags & 3)) {
           // ---- tile end: every append of this tile by the row group's four warps is complete and visible
           // (the periodic mask is taken by ONE warp of the row group before the barrier -- it may miss this tile's last
           // appends of the other warps, which is harmless -- so that all four warps act on the same rows)
@@ -846,7 +849,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (++tslot == 3) tslot = 0;
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
-      if (P.dump == nullptr && P.pilot_mode == 0) {
+      if (!kPilot && P.dump == nullptr) {
         // unit end: leave a sorted prefix, publish it and refine the row's shared threshold, so that the units
         // that scan this row later start from everything this stream has learnt
         // (streams that learnt almost nothing in this unit skip it: their few keys still reach the final merge)
@@ -865,7 +868,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       }
     }
     if (warp == 4 && lane == 0) *s_poll = -1;       // releases the poller warp
-    if (P.stat_candidates != nullptr && P.dump == nullptr && P.pilot_mode == 0) {
+    if (!kPilot && P.stat_candidates != nullptr && P.dump == nullptr) {
       const unsigned a = __reduce_add_sync(kFull, stat_appends);
       if (lane == 0) {
         atomicAdd(P.stat_candidates + 1, static_cast<unsigned long long>(a));
@@ -892,41 +895,32 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
 
 }  // namespace
 
-cudaError_t launch_scan_tc(const ScanParams& P, const void* tmap_q, const void* tmap_e, int cta_group, int n_groups,
-                           cudaStream_t stream, const void* tmap_ql, const void* tmap_el) {
+// One variant of the kernel, launched as clusters of CG CTAs.  The variants are instantiated in separate translation units
+// (bb_scan_tc_*.cu) so that they compile in parallel: one instantiation is ~70k SASS instructions.
+template <int CG, bool kRowCons, bool kSplit, bool kPilot>
+cudaError_t launch_scan_tc_variant(const ScanParams& P, const void* tmap_q, const void* tmap_e, const void* tmap_ql, const void* tmap_el,
+                                   int n_groups, cudaStream_t stream) {
   const CUtensorMap* tq = static_cast<const CUtensorMap*>(tmap_q);
   const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e);
-  const bool split = tmap_ql != nullptr && tmap_el != nullptr;
-  const CUtensorMap* tql = split ? static_cast<const CUtensorMap*>(tmap_ql) : tq;
-  const CUtensorMap* tel = split ? static_cast<const CUtensorMap*>(tmap_el) : te;
+  const CUtensorMap* tql = kSplit ? static_cast<const CUtensorMap*>(tmap_ql) : tq;
+  const CUtensorMap* tel = kSplit ? static_cast<const CUtensorMap*>(tmap_el) : te;
+  auto kernel = scan_tc_kernel<CG, kRowCons, kSplit, kPilot>;
+  constexpr int smem = Cfg<CG, kRowCons>::kSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kThreads);
   cfg.stream = stream;
-  const bool row_cons = P.cons != nullptr && P.class_valid == nullptr;
-  auto launch = [&](auto kernel, int smem, int cg) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    cfg.gridDim = dim3(n_groups * cg);
-    cfg.dynamicSmemBytes = smem;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cg;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, *tq, *te, *tql, *tel, P, n_groups);
-  };
-  if (cta_group == 2) {
-    if (split) return row_cons ? launch(scan_tc_kernel<2, true, true>, Cfg<2, true>::kSmemBytes, 2)
-                               : launch(scan_tc_kernel<2, false, true>, Cfg<2, false>::kSmemBytes, 2);
-    return row_cons ? launch(scan_tc_kernel<2, true, false>, Cfg<2, true>::kSmemBytes, 2)
-                    : launch(scan_tc_kernel<2, false, false>, Cfg<2, false>::kSmemBytes, 2);
-  }
-  if (split) return row_cons ? launch(scan_tc_kernel<1, true, true>, Cfg<1, true>::kSmemBytes, 1)
-                             : launch(scan_tc_kernel<1, false, true>, Cfg<1, false>::kSmemBytes, 1);
-  return row_cons ? launch(scan_tc_kernel<1, true, false>, Cfg<1, true>::kSmemBytes, 1)
-                  : launch(scan_tc_kernel<1, false, false>, Cfg<1, false>::kSmemBytes, 1);
+  cfg.gridDim = dim3(n_groups * CG);
+  cfg.dynamicSmemBytes = smem;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, *tq, *te, *tql, *tel, P, n_groups);
 }
 
 }  // namespace bb

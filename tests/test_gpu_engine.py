@@ -565,7 +565,7 @@ def test_small_batch_exact_path_matches_tile_scan(bb):
         descs, specs = _scenario_descs(bb, eng, themes, rated, b)
         kw = dict(q_item=q_items, q_cf=u, w_content=0.4, w_cf=0.6, constraints=descs, self_id=q_items, precision="fp32")
         s1, i1 = eng.search(k, **kw)
-        assert eng.info()["last_units"] == b * min(64, max(1, -(-n // 4096)))          # the small path ran
+        assert eng.info()["last_units"] == b * min(128, max(1, -(-n // 1024)))         # the small path ran
         os.environ["BB_NO_SMALL"] = "1"
         try:
             s2, i2 = eng.search(k, **kw)

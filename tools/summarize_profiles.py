@@ -24,13 +24,13 @@ for r in rows[1:]:
     seq.append((name, ns))
     per.setdefault(name, []).append(ns)
 with open(os.path.join(out, f"{tag}_launches_summary.txt"), "w") as f:
-    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'scan_|prep_|merge_|fill_u32|pack_meta|mask_kernel' "
-            "-c 400 python bench.py --steps 2 --warmup 1 --no-cpu-baseline\n"
+    f.write("ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:scan_tc|merge_|prep_|mask_kernel|seed_' "
+            "-c 60 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-check\n"
             "(per-launch times are cold-cache and serialised under the profiler: compare SHARES, not absolutes)\n\n")
     f.write(f"{'kernel':26s} {'launches':>8s} {'total ms':>10s} {'mean ms':>10s}\n")
     for n, v in per.items():
         f.write(f"{n:26s} {len(v):8d} {sum(v) / 1e6:10.3f} {sum(v) / len(v) / 1e6:10.3f}\n")
-    step_names = ("prep_queries_kernel", "fill_u32_kernel", "mask_kernel", "scan_tc_kernel", "scan_fp32_kernel", "merge_emit_kernel")
+    step_names = ("prep_queries_kernel", "seed_thresholds_kernel", "mask_kernel", "scan_tc_kernel", "scan_fp32_kernel", "merge_emit_kernel")
     last_merge = max(i for i, (n, _) in enumerate(seq) if n.startswith("merge_emit_kernel"))
     first = max(i for i, (n, _) in enumerate(seq[:last_merge]) if n.startswith("prep_queries_kernel"))
     step = [x for x in seq[first:last_merge + 1] if x[0].startswith(step_names)]
@@ -44,7 +44,8 @@ print(open(os.path.join(out, f"{tag}_launches_summary.txt")).read())
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rr[0], rr[1], rr[-1]
-want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__cluster_size",
+want = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_elapsed.avg.per_second", "launch__grid_size", "launch__block_size", "launch__cluster_size",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -80,6 +81,7 @@ with open(os.path.join(out, f"{tag}_scan_tc_ncu_full.txt"), "w") as f:
         st = {k.replace("stall_", ""): int(r[six[k]] or 0) for k in sh if k.startswith("stall_") and "Not Issued" not in k}
         st = {k: v for k, v in st.items() if v > 0.05 * max(1, int(r[six["# Samples"]]))}
         f.write(f"  {int(r[six['# Samples']]):8d}  exec={r[six['Instructions Executed']]:>12s}  {r[six['Source']].strip()[:70]:70s} {st}\n")
-json.dump({"kernel": "scan_tc_kernel<2>", "dram_bytes_per_launch": dram, "source": f"profiles/{tag}_scan_tc_ncu_full.txt"},
+json.dump({"kernel": "scan_tc_kernel<2,0,0>", "per_n_gpus": {"1": dram}, "source": f"profiles/{tag}_scan_tc_ncu_full.txt",
+           "note": "one ncu --set full capture per GPU count; bench.py prints null for counts that were not captured"},
           open(os.path.join(out, "scan_dram_bytes.json"), "w"))
 print(open(os.path.join(out, f"{tag}_scan_tc_ncu_full.txt")).read()[:3000])
