@@ -324,24 +324,38 @@ Plan make_plan(const bb_handle* h, int n_queries, bool tc) {
   if (s_lo < s_fill) s_lo = s_fill;
   if (s_lo < 1) s_lo = 1;
   if (s_lo > s_cap) s_lo = s_cap;
-  // Cost of a static round-robin schedule in tile times: rounds x (tiles per unit + F), F = the fixed price of a unit
-  // (query operand load, pipeline fill, candidate-stream start and its sorted + published prefix at the end: ~8 tile
-  // times).  Large catalogs: many long units, the term only breaks ties between equally full schedules.  Small
-  // catalogs (25k rows = 99 tiles): ONE round of 64 long units beats two rounds of 144 short ones.
   long long splits = s_lo;
-  double best = 1e300;
-  long long w_lo = (s_lo - 8 > s_fill) ? s_lo - 8 : (s_fill < s_lo ? s_fill : s_lo);
-  if (tc && w_lo > (s_fill + 1) / 2) w_lo = (s_fill + 1) / 2;
-  if (w_lo < 1) w_lo = 1;
-  const double fixed = 8.0;
-  for (long long sc = w_lo; sc <= s_cap && sc <= s_lo + 16; ++sc) {
-    const long long units = sc * p.n_qblocks;
-    const long long rounds = (units + hw_groups - 1) / hw_groups;
-    const double tiles = static_cast<double>((p.n_tiles + sc - 1) / sc);
-    const double cost = static_cast<double>(rounds) * (tiles + fixed) + 0.001 * static_cast<double>(sc > s_lo ? sc - s_lo : s_lo - sc);
-    if (cost < best - 1e-9) {
-      best = cost;
-      splits = sc;
+  const long long s_len = p.n_tiles / (65536 / p.tile_items);
+  if (tc && s_len < s_fill) {
+    // Small catalog (fewer than ~64k rows per unit even with the fewest splits that fill the machine; 25k rows = 99
+    // tiles): every unit pays a fixed price F of ~8 tile times (query operand load, pipeline fill, candidate-stream start
+    // and end), so minimize rounds x (tiles per unit + F) -- ONE round of 64 long units beats two rounds of 144 short ones.
+    double best = 1e300;
+    const double fixed = 8.0;
+    for (long long sc = (s_fill + 1) / 2 > 1 ? (s_fill + 1) / 2 : 1; sc <= s_cap && sc <= s_fill + 16; ++sc) {
+      const long long units = sc * p.n_qblocks;
+      const long long rounds = (units + hw_groups - 1) / hw_groups;
+      const double cost = static_cast<double>(rounds) * (static_cast<double>((p.n_tiles + sc - 1) / sc) + fixed);
+      if (cost < best - 1e-9) {
+        best = cost;
+        splits = sc;
+      }
+    }
+  } else {
+    // Large catalog: units of ~64k rows; among the split counts near that target pick the one whose static round-robin
+    // schedule keeps the most CTA groups busy.
+    double best = -1.0;
+    const long long w_lo = (s_lo - 8 > s_fill) ? s_lo - 8 : (s_fill < s_lo ? s_fill : s_lo);
+    for (long long sc = w_lo; sc <= s_cap && sc <= s_lo + 16; ++sc) {
+      const long long units = sc * p.n_qblocks;
+      const long long rounds = (units + hw_groups - 1) / hw_groups;
+      // occupancy of the static schedule, with a mild preference for the target unit length
+      const double eff = static_cast<double>(units) / static_cast<double>(rounds * hw_groups) -
+                         0.001 * static_cast<double>(sc > s_lo ? sc - s_lo : s_lo - sc);
+      if (eff > best + 1e-9) {
+        best = eff;
+        splits = sc;
+      }
     }
   }
   if (const char* ov = getenv("BB_SPLITS")) {      // experimentation override

@@ -598,7 +598,8 @@ seed_thresholds_kernel(const ScanParams P, int64_t pilot_items) {
   }
   mg.flush();
   // listed ids inside the pilot range (they may sit behind up to E of the maxima)
-  // (a single list per query is walked exactly by the pilot's epilogue: nothing to allow for)
+  // (a single list per query is walked exactly by the pilot's epilogue -- the pilot only runs on the variant that walks
+  // lists: nothing to allow for)
   int64_t excl = 0;
   if (lane == 0 && P.q_excl_n > 1) {
     for (int e = 0; e < P.q_excl_n; ++e) {

@@ -597,9 +597,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       // a merge: the warp visits its columns in increasing order, so the lane keeps the next listed id (as a local
       // row) and a cursor; listed columns are removed from the pass bitmap BEFORE the vote and cost the slow path
       // nothing.  More than one list per query falls back to a binary search per passing candidate.
+      // (the per-row-descriptor variant is short of registers: it keeps the per-candidate search)
+      constexpr bool kWalk = !kRowCons;
       bool excl_only = false;
       int ex_next = INT32_MAX, ex_i = 0;             // next listed LOCAL row >= the columns seen so far; its index in the list
-      if (q_valid && P.q_excl_n == 1) {
+      if (kWalk && q_valid && P.q_excl_n == 1) {
         const int32_t l = __ldg(P.q_excl + q);
         if (l >= 0) {
           const int64_t lo = __ldg(P.excl_off + l), hi = __ldg(P.excl_off + l + 1);
@@ -615,7 +617,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             ex_next = r < INT32_MAX ? static_cast<int>(r) : INT32_MAX;
           }
         }
-      } else if (q_valid && P.q_excl_n > 1) {
+      } else if (q_valid && P.q_excl_n > (kWalk ? 1 : 0)) {
         for (int e = 0; e < P.q_excl_n; ++e) excl_only |= __ldg(P.q_excl + static_cast<int64_t>(q) * P.q_excl_n + e) >= 0;
       }
       const uint32_t* class_row = nullptr;           // this row's constraint-set validity bitmap (class mode)
@@ -716,7 +718,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           }
           // columns of this chunk that the row's exclusion list names (rare: a cursor compare per chunk)
           unsigned ex_mask = 0u;
-          {
+          if constexpr (kWalk) {
             const int64_t c_lo = item0 + chunk * 32;
             while (static_cast<int64_t>(ex_next) < c_lo + 32) {
               if (static_cast<int64_t>(ex_next) >= c_lo) ex_mask |= 1u << static_cast<int>(ex_next - c_lo);
