@@ -18,14 +18,14 @@
 // Algorithmic work (sparse): sum_u nnz_u^2 multiply-adds; bytes >= nnz * 8.  The first version (global reductions into
 // a dense 2.5 GB Gram + a streaming select) took 27.5 ms at 1M users x 25,216 items and was bound by same-address
 // atomics; this one is bound by shared-memory atomic throughput.
+#include <cstdlib>
 #include "bb_common.cuh"
 #include "bb_kernels.h"
 
 namespace bb {
 namespace {
 
-constexpr int kAccThreads = 1024;                 // threads of the accumulate / sort CTAs (latency-bound gathers: more warps in flight)
-constexpr int kAccWarps = kAccThreads / 32;
+constexpr int kAccThreads = 1024;                 // threads of the counting-sort CTAs (latency-bound gathers: more warps in flight)
 constexpr int kSortCtas = 148;                    // CTAs of the counting sort (one per SM)
 constexpr int kSmemHistItems = 56 * 1024;         // largest item count whose uint32 histogram fits in shared memory
 
@@ -100,7 +100,7 @@ __global__ void ii_column_prefix_kernel(uint32_t* __restrict__ block_hist, const
     s += block_sq[static_cast<int64_t>(g) * n_items + i];
   }
   col_cnt[i] = run;
-  sq[i] = sqrtf(s);                               // the item's L2 norm (what the cosine divides by)
+  sq[i] = s > 0.f ? 1.f / sqrtf(s) : 0.f;         // 1 / the item's L2 norm (what the cosine multiplies by)
 }
 
 // single-block exclusive scan (n_items is catalog sized; this is microseconds)
@@ -156,7 +156,7 @@ ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
 
 __global__ void ii_sqrt_kernel(float* __restrict__ sq, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) sq[i] = sqrtf(sq[i]);
+  if (i < n) sq[i] = sq[i] > 0.f ? 1.f / sqrtf(sq[i]) : 0.f;
 }
 
 // ---- fallback for catalogs whose histogram does not fit in shared memory: global atomics
@@ -203,9 +203,11 @@ __global__ void ii_bucket_scatter_kernel(const unsigned long long* __restrict__ 
   order[atomicAdd(bucket_pos + (63 - b), 1)] = i;
 }
 // unit_off[p] = first unit of the p-th item of `order`; hot_of[item] = row of the item in the partial-row buffer
-// (-1 for single-unit items).  counters[0] = number of units, counters[1] = number of hot items.  Single block.
+// (-1 for single-unit items); unit_tab[u] = (item, chunk index, units of the item, hot row).  counters[0] = number of
+// units, counters[1] = number of hot items, counters[3] = integer accumulators, counters[7] = packed ratings.  Single block.
 __global__ void ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* __restrict__ order, int n,
-                                int chunk, int* __restrict__ unit_off, int* __restrict__ hot_of, int* __restrict__ counters) {
+                                int chunk, int* __restrict__ unit_off, int* __restrict__ hot_of, int4* __restrict__ unit_tab,
+                                int* __restrict__ counters) {
   __shared__ int part_u[1024], part_h[1024];
   const int t = threadIdx.x;
   const int per = (n + 1023) / 1024;
@@ -235,6 +237,8 @@ __global__ void ii_units_kernel(const unsigned long long* __restrict__ col_cnt, 
     const long long dmax = n > 0 ? 2 * (static_cast<long long>(col_cnt[order[0]]) + 1) : 1;
     const long long vm = counters[5];
     counters[3] = (counters[4] == 0 && counters[6] == 1 && vm * vm * dmax < (1ll << 31)) ? 1 : 0;
+    // packed ratings: (item | rating << 24) in one word per rating (ii_pack_kernel)
+    counters[7] = (counters[3] != 0 && vm < 256 && n <= (1 << 24)) ? 1 : 0;
   }
   __syncthreads();
   int ru = part_u[t], rh = part_h[t];
@@ -243,10 +247,21 @@ __global__ void ii_units_kernel(const unsigned long long* __restrict__ col_cnt, 
     const long long d = static_cast<long long>(col_cnt[item]);
     const int units = d <= chunk ? 1 : static_cast<int>((d + chunk - 1) / chunk);
     unit_off[p] = ru;
-    hot_of[item] = units > 1 ? rh : -1;
+    const int hot = units > 1 ? rh : -1;
+    hot_of[item] = hot;
+    for (int c = 0; c < units; ++c) unit_tab[ru + c] = make_int4(item, c, units, hot);
     ru += units;
     rh += units > 1;
   }
+}
+
+// small non-negative integer ratings: one word per rating halves the accumulate pass's row reads (and the packed
+// matrix of config 3, 78 MB, stays in L2)
+__global__ void ii_pack_kernel(const int32_t* __restrict__ indices, const float* __restrict__ values, int64_t nnz,
+                               const int* __restrict__ counters, uint32_t* __restrict__ packed) {
+  if (counters[7] == 0) return;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz; e += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    packed[e] = static_cast<uint32_t>(__ldg(indices + e)) | (static_cast<uint32_t>(__ldg(values + e)) << 24);
 }
 
 __global__ void ii_zero_hot_kernel(float* __restrict__ hot_rows, int* __restrict__ hot_done, const int* __restrict__ counters,
@@ -313,60 +328,116 @@ struct IIMerger {          // per-warp running top-128 (same scheme as the scan 
     __syncwarp();
     if (n_new + 32 > kCap / 2) flush();
   }
-  // top-128 of this merger's sorted prefix and another warp's sorted prefix (one step of the tree merge)
-  __device__ void absorb_sorted(const uint64_t* other) {
-    constexpr int PE = kEpl / 2;
-    uint64_t p[PE];
-#pragma unroll
-    for (int i = 0; i < PE; ++i) {
-      const int e = (i << 5) | lane;
-      const uint64_t r = other[kCap / 2 - 1 - e];
-      const uint64_t a = stage[e];
-      p[i] = a > r ? a : r;
-    }
-    __syncwarp();
-    warp_bitonic_merge_desc<PE>(p, lane);
-#pragma unroll
-    for (int i = 0; i < PE; ++i) stage[(i << 5) | lane] = p[i];
-    __syncwarp();
-  }
 };
 
-// normalize + select the range [j0, j1) of item i's Gram row (`row` in shared or global memory) into the warp mergers.
-// Four strides per step: the norm loads of the four keys are independent of the mergers' state and overlap.
-template <bool kGlobal, bool kInt>
-__device__ __forceinline__ void ii_select_range(const float* row, int i, float norm_i, const float* __restrict__ norm, int j0, int j1,
-                                                IIMerger& mg, int warp, int lane) {
-  constexpr int U = 4;
-  const int n = j1 - j0;
-  for (int base = warp * 32; base < n; base += kAccThreads * U) {
-    uint64_t key[U];
+// ---- selection of item i's top-k from a Gram-row range held in shared memory.
+// Round 1/2a kept a top-128 per warp (32 mergers, 256-key sort networks, a 5-level tree merge): 5.6G warp instructions
+// for 405M multiply-adds at config 3, i.e. the pass was bound by the sort networks.  Now:
+//   pass A  every thread turns its entries into cosines in place (four per shared-memory read) and keeps its best;
+//   bound   T = k-th largest of the thread bests (each is the score of a distinct item, so at least k items reach T):
+//           per-warp 32-key sorts, then warp 0 pops k times from the heads of the sorted lists;
+//   pass C  entries >= T go to a small CTA buffer that warp 0 drains into ONE merger; everything that was handled is
+//           zeroed (the accumulator is clean for the next unit), an entry that found the buffer full stays and the pass
+//           repeats (only the <= k threads whose best reaches T hold survivors: a repeat is the rare case).
+constexpr int kSelBuf = 1024;                      // keys of the survivor buffer (aliases the per-warp sorted bests)
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int jj = base + u * kAccThreads + lane;
-      key[u] = 0ull;
-      if (jj < n) {
-        const float g = kGlobal ? __ldcg(row + jj) : (kInt ? static_cast<float>(reinterpret_cast<const unsigned*>(row)[jj]) : row[jj]);
-        const int j = j0 + jj;
-        if (g > 0.f && j != i) key[u] = make_key(g / (norm_i * __ldg(norm + j)), static_cast<uint32_t>(j));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) mg.offer(key[u]);
+  for (int d = 16; d > 0; d >>= 1) {
+    const uint64_t o = __shfl_xor_sync(kFull, v, d);
+    v = o > v ? o : v;
   }
+  return v;
 }
 
-// Tree merge of the kAccWarps sorted per-warp tops (all warps call; ends with the CTA's top-128 in stages[0..127]).
-__device__ __forceinline__ void ii_tree_merge(uint64_t* stages, IIMerger& mg, int warp) {
-#pragma unroll 1
-  for (int s = 1; s < kAccWarps; s <<= 1) {
-    __syncthreads();
-    if ((warp & (2 * s - 1)) == 0) mg.absorb_sorted(stages + (warp + s) * kCap);
+struct IISelShared {       // static shared state of the selection
+  unsigned long long thr;  // T as a key
+  int cnt;                 // survivors appended in this round
+  int more;                // some survivors did not fit: repeat pass C
+};
+
+template <int kThreads, bool kInt>
+__device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i, float inv_i, const float* __restrict__ inv_norm, int k,
+                                               uint64_t* buf, IISelShared* sh, IIMerger& mg, uint64_t& thr, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int n4 = (n + 3) >> 2;                     // (entries in [n, range) are never written: they stay zero)
+  uint4* acc4 = reinterpret_cast<uint4*>(acc);
+  // pass A
+  float best_c = 0.f;
+  int best_j = 0;
+  for (int q = tid; q < n4; q += kThreads) {
+    const uint4 w = acc4[q];
+    if ((w.x | w.y | w.z | w.w) != 0u) {
+      const unsigned wu[4] = {w.x, w.y, w.z, w.w};
+      float c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + q * 4 + u;
+        c[u] = 0.f;
+        if (wu[u] != 0u) {
+          const float g = kInt ? static_cast<float>(wu[u]) : __uint_as_float(wu[u]);
+          if (g > 0.f && j != i) c[u] = g * (inv_i * __ldg(inv_norm + j));
+          if (c[u] > best_c) { best_c = c[u]; best_j = j; }       // ascending j: ties keep the lower id
+        }
+      }
+      reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
+    }
+  }
+  uint64_t v[1] = {best_c > 0.f ? make_key(best_c, static_cast<uint32_t>(best_j)) : 0ull};
+  warp_sort_desc<1>(v, lane);
+  buf[warp * 32 + lane] = v[0];
+  __syncthreads();
+  if (warp == 0) {
+    int ptr = 0;
+    uint64_t head = lane < kWarps ? buf[lane * 32] : 0ull;
+    uint64_t m = 0ull;
+    for (int it = 0; it < k; ++it) {
+      m = warp_max_u64(head);
+      if (m == 0ull) break;
+      if (head == m) { ++ptr; head = ptr < 32 ? buf[lane * 32 + ptr] : 0ull; }
+    }
+    if (lane == 0) { sh->thr = m > thr ? m : thr; sh->cnt = 0; sh->more = 0; }
   }
   __syncthreads();
+  thr = sh->thr;
+  const float thr_c = thr != 0ull ? key_score(thr) : 0.f;
+  // pass C
+  while (true) {
+    for (int q = tid; q < n4; q += kThreads) {
+      const float4 w = reinterpret_cast<const float4*>(acc)[q];
+      if (w.x != 0.f || w.y != 0.f || w.z != 0.f || w.w != 0.f) {
+        float c[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c[u] >= thr_c && c[u] > 0.f) {
+            const uint64_t key = make_key(c[u], static_cast<uint32_t>(j0 + q * 4 + u));
+            if (key >= thr) {
+              const int pos = atomicAdd(&sh->cnt, 1);
+              if (pos < kSelBuf) { buf[pos] = key; c[u] = 0.f; }
+            } else {
+              c[u] = 0.f;
+            }
+          } else {
+            c[u] = 0.f;
+          }
+        }
+        reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int appended = sh->cnt;
+      const int cnt = min(appended, kSelBuf);
+      for (int x = 0; x < cnt; x += 32) mg.offer(x + lane < cnt ? buf[x + lane] : 0ull);
+      if (lane == 0) { sh->cnt = 0; sh->more = appended > kSelBuf; }
+    }
+    __syncthreads();
+    if (sh->more == 0) break;                      // (written again only after the next barrier)
+  }
 }
 
-// warp 0 writes item i's lists from the CTA's sorted top (stages[0..127]): positives first, then zero-similarity items
+// warp 0 writes item i's lists from its merger's sorted top (s0[0..127]): positives first, then zero-similarity items
 // by ascending id
 __device__ __forceinline__ void ii_emit(const uint64_t* s0, int i, int n_items, int k, int lane, float* __restrict__ out_scores,
                                         int32_t* __restrict__ out_ids) {
@@ -397,101 +468,132 @@ __device__ __forceinline__ void ii_emit(const uint64_t* s0, int i, int n_items, 
   }
 }
 
-__global__ void __launch_bounds__(kAccThreads)
+// One CTA per work unit (item i, chunk of its raters), units handed out by a global counter, hot items first.
+// Accumulate: raters are dealt to the warps cyclically (rater e_begin + x goes to warp x % kWarps), so an item with a
+// few dozen raters still keeps every warp busy.  Per step a warp holds 32 raters -- lane l has (user row start, length,
+// rating) of one, the NEXT step's 32 are already being fetched -- and walks their rows as ONE flattened element range,
+// lane per element: the owning rater of element e is the number of rows that end at or before e, i.e. a running base
+// plus the population count of the window's row-end bitmap (one redux.or per 32 elements) below the lane.  All 32 lanes
+// work on ~20-entry rows and consecutive windows are independent, so several row reads stay in flight per warp.
+struct IIRaters {
+  int64_t p0;      // start of the rater's row in the rating arrays
+  int len;         // row length
+  unsigned r;      // the rater's rating of item i (integer mode: the integer; else float bits)
+};
+
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-                     const long long* __restrict__ col_ptr, const int2* __restrict__ csc,
-                     const float* __restrict__ norm, const int32_t* __restrict__ order, const int* __restrict__ unit_off,
-                     const int* __restrict__ hot_of, const int* __restrict__ counters, int n_items, int range, int chunk, int k,
-                     int max_hot, float* __restrict__ hot_rows, int* __restrict__ hot_done, int* __restrict__ work_counter,
-                     float* __restrict__ out_scores, int32_t* __restrict__ out_ids) {
+                     const uint32_t* __restrict__ packed, const long long* __restrict__ col_ptr, const int2* __restrict__ csc,
+                     const float* __restrict__ inv_norm, const int4* __restrict__ unit_tab, const int* __restrict__ counters,
+                     int n_items, int range, int chunk, int k, int max_hot, float* __restrict__ hot_rows, int* __restrict__ hot_done,
+                     int* __restrict__ work_counter, float* __restrict__ out_scores, int32_t* __restrict__ out_ids) {
+  constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char ii_smem[];
-  float* acc = reinterpret_cast<float*>(ii_smem);                                   // [range]
-  uint64_t* stages = reinterpret_cast<uint64_t*>(ii_smem + static_cast<size_t>(range) * 4);   // [kAccWarps][kCap]
-  __shared__ int s_unit, s_last;
+  float* acc = reinterpret_cast<float*>(ii_smem);                                   // [range], zero between units
+  uint64_t* buf = reinterpret_cast<uint64_t*>(ii_smem + static_cast<size_t>(range) * 4);   // [kSelBuf]
+  uint64_t* mstage = buf + kSelBuf;                                                 // [kCap]: warp 0's merger
+  __shared__ int s_unit[2], s_last;
+  __shared__ IISelShared s_sel;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_units = counters[0];
   const bool int_mode = counters[3] != 0;          // every rating is a small non-negative integer (set by ii_units_kernel)
+  const bool use_packed = counters[7] != 0;
+  for (int j = tid; j < range; j += kThreads) acc[j] = 0.f;
+  if (tid == 0) s_unit[0] = atomicAdd(work_counter, 1);
+  __syncthreads();
 
-  while (true) {
-    if (tid == 0) s_unit = atomicAdd(work_counter, 1);
-    __syncthreads();
-    const int unit = s_unit;
-    __syncthreads();
+  for (int it = 0;; ++it) {
+    const int unit = s_unit[it & 1];
     if (unit >= n_units) break;
-    // unit -> (position in `order`, chunk of the item's raters)
-    int lo = 0, hi = n_items;                      // largest p with unit_off[p] <= unit
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(unit_off + mid) <= unit) lo = mid; else hi = mid;
-    }
-    const int i = __ldg(order + lo);
-    const int c_idx = unit - __ldg(unit_off + lo);
-    const int n_item_units = __ldg(unit_off + lo + 1) - __ldg(unit_off + lo);
+    if (tid == 0) s_unit[(it + 1) & 1] = atomicAdd(work_counter, 1);     // the next unit's ticket travels while this one runs
+    const int4 ut = __ldg(unit_tab + unit);
+    const int i = ut.x, c_idx = ut.y, n_item_units = ut.z, hot = ut.w;
     const long long e_begin = __ldg(col_ptr + i) + static_cast<long long>(c_idx) * chunk;
     const long long e_end = min(__ldg(col_ptr + i + 1), e_begin + chunk);
-    const int hot = __ldg(hot_of + i);
     const bool single = n_item_units == 1;
-    const float norm_i = __ldg(norm + i);
+    const float inv_i = __ldg(inv_norm + i);
     IIMerger mg;
-    if (single) mg.init(stages + warp * kCap, lane);
+    uint64_t thr = 0ull;
+    if (single && warp == 0) mg.init(mstage, lane);
 
     for (int j0 = 0; j0 < n_items; j0 += range) {
       const int j1 = min(n_items, j0 + range);
-      for (int j = tid; j < j1 - j0; j += kAccThreads) acc[j] = 0.f;
-      __syncthreads();
-      // Raters are dealt to the warps cyclically (rater e_begin + x goes to warp x % 32), so an item with a few dozen
-      // raters still keeps every warp busy.  Per step a warp prefetches up to 32 of its raters at once -- lane l holds
-      // (user, rating, row bounds) of one -- then walks those rows one after the other with coalesced row reads; the
-      // loads of row r+1 do not depend on the atomics of row r, so the unrolled loop keeps several rows in flight.
       const long long n_raters = e_end - e_begin;
-      for (long long x0 = 0; x0 * kAccWarps + warp < n_raters; x0 += 32) {
-        const long long mine = (x0 + lane) * kAccWarps + warp;
-        int64_t p0 = 0;
-        int len = 0;
-        float r_ui = 0.f;
+      auto fetch = [&](long long x0) {
+        IIRaters f = {0, 0, 0u};
+        const long long mine = (x0 + lane) * kWarps + warp;
         if (mine < n_raters) {
           const int2 ur = __ldg(csc + e_begin + mine);
-          r_ui = __int_as_float(ur.y);
-          p0 = __ldg(indptr + ur.x);
-          len = static_cast<int>(__ldg(indptr + ur.x + 1) - p0);
+          f.r = int_mode ? static_cast<unsigned>(__int_as_float(ur.y)) : static_cast<unsigned>(ur.y);
+          f.p0 = __ldg(indptr + ur.x);
+          f.len = static_cast<int>(__ldg(indptr + ur.x + 1) - f.p0);
         }
-        const int n_r = __popc(__ballot_sync(kFull, mine < n_raters));
-#pragma unroll 4
-        for (int r = 0; r < n_r; ++r) {
-          const int64_t q0 = __shfl_sync(kFull, p0, r);
-          const int ln = __shfl_sync(kFull, len, r);
-          const float rr = __shfl_sync(kFull, r_ui, r);
-          for (int t = lane; t < ln; t += 32) {
-            const int32_t j = __ldg(indices + q0 + t);
-            const float v = __ldg(values + q0 + t);
-            if (j >= j0 && j < j1) {
-              // integral ratings (the usual 1..5 stars): native integer shared-memory atomics; a float atomicAdd on
-              // shared memory is a compare-and-swap loop that spins on popular items
-              if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (j - j0), static_cast<unsigned>(rr * v));
-              else atomicAdd(acc + (j - j0), rr * v);
+        return f;
+      };
+      IIRaters cur = fetch(0);
+      for (long long x0 = 0; x0 * kWarps + warp < n_raters; x0 += 32) {
+        const IIRaters nxt = fetch(x0 + 32);
+        int incl = cur.len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        const int64_t abase = cur.p0 - (incl - cur.len);       // element e of the flattened range lives at abase + e
+        int rbase = 0;                                         // rows that end before the window
+#pragma unroll 2
+        for (int e0 = 0; e0 < total; e0 += 32) {
+          const int d = incl - e0;
+          const unsigned ends = __reduce_or_sync(kFull, (d >= 0 && d < 32) ? (1u << d) : 0u);
+          const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
+          rbase += __popc(ends);
+          const int e = e0 + lane;
+          const int64_t q = __shfl_sync(kFull, abase, r) + e;
+          const unsigned rr = __shfl_sync(kFull, cur.r, r);
+          if (e < total) {
+            if (use_packed) {
+              const uint32_t w = __ldg(packed + q);
+              const int j = static_cast<int>(w & 0xffffffu);
+              if (j >= j0 && j < j1) atomicAdd(reinterpret_cast<unsigned*>(acc) + (j - j0), rr * (w >> 24));
+            } else {
+              const int32_t j = __ldg(indices + q);
+              const float v = __ldg(values + q);
+              if (j >= j0 && j < j1) {
+                // integral ratings (the usual 1..5 stars): native integer shared-memory atomics; a float atomicAdd on
+                // shared memory is a compare-and-swap loop that spins on popular items
+                if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (j - j0), rr * static_cast<unsigned>(v));
+                else atomicAdd(acc + (j - j0), __uint_as_float(rr) * v);
+              }
             }
           }
         }
+        cur = nxt;
       }
       __syncthreads();
       if (single) {
-        if (int_mode) ii_select_range<false, true>(acc, i, norm_i, norm, j0, j1, mg, warp, lane);
-        else ii_select_range<false, false>(acc, i, norm_i, norm, j0, j1, mg, warp, lane);
-      } else if (hot >= 0 && hot < max_hot) {
+        if (int_mode) ii_select_smem<kThreads, true>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr, tid);
+        else ii_select_smem<kThreads, false>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr, tid);
+      } else {
         float* row = hot_rows + static_cast<int64_t>(hot) * n_items + j0;
-        for (int j = tid; j < j1 - j0; j += kAccThreads) {
+        const bool add = hot >= 0 && hot < max_hot;
+        for (int j = tid; j < j1 - j0; j += kThreads) {
           const float v = int_mode ? static_cast<float>(reinterpret_cast<const unsigned*>(acc)[j]) : acc[j];
-          if (v != 0.f) atomicAdd(row + j, v);       // coalesced fire-and-forget reductions (result unused -> RED)
+          if (v != 0.f) {
+            if (add) atomicAdd(row + j, v);          // coalesced fire-and-forget reductions (result unused -> RED)
+            acc[j] = 0.f;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
 
     if (single) {
-      mg.flush();
-      ii_tree_merge(stages, mg, warp);
-      if (warp == 0) ii_emit(stages, i, n_items, k, lane, out_scores, out_ids);
-      __syncthreads();
+      if (warp == 0) {
+        mg.flush();
+        ii_emit(mstage, i, n_items, k, lane, out_scores, out_ids);
+      }
     } else {
       // the unit of a hot item that finishes last selects from the completed global row
       __threadfence();
@@ -500,26 +602,37 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
       __syncthreads();
       if (s_last) {
         __threadfence();
-        mg.init(stages + warp * kCap, lane);
-        ii_select_range<true, false>(hot_rows + static_cast<int64_t>(hot) * n_items, i, norm_i, norm, 0, n_items, mg, warp, lane);
-        mg.flush();
-        ii_tree_merge(stages, mg, warp);
-        if (warp == 0) ii_emit(stages, i, n_items, k, lane, out_scores, out_ids);
+        if (warp == 0) mg.init(mstage, lane);
+        for (int j0 = 0; j0 < n_items; j0 += range) {
+          const int j1 = min(n_items, j0 + range);
+          const float* row = hot_rows + static_cast<int64_t>(hot) * n_items + j0;
+          for (int j = tid; j < j1 - j0; j += kThreads) acc[j] = __ldcg(row + j);
+          __syncthreads();
+          ii_select_smem<kThreads, false>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr, tid);
+        }
+        if (warp == 0) {
+          mg.flush();
+          ii_emit(mstage, i, n_items, k, lane, out_scores, out_ids);
+        }
       }
-      __syncthreads();
     }
+    __syncthreads();                               // the next ticket is visible; warp 0 is done with its merger stage
   }
 }
 
-// raters per work unit: 2048, raised so that the partial-row buffer (<= nnz / chunk hot items x n_items floats) stays
+// raters per work unit: 8192 (BB_II_CHUNK), raised so that the partial-row buffer (<= nnz / chunk hot items x n_items floats) stays
 // within 1 GiB
 int ii_chunk(int n_items, int64_t nnz) {
-  long long chunk = 2048;
+  static const long long base = [] { const char* v = getenv("BB_II_CHUNK"); const long long c = v ? atoll(v) : 0; return c >= 256 ? c : 8192; }();
+  long long chunk = base;
   const long long budget_rows = (1ll << 30) / (static_cast<long long>(n_items) * 4 + 1);
   if (budget_rows > 0 && nnz / chunk > budget_rows) chunk = (nnz + budget_rows - 1) / budget_rows;
-  if (chunk < 2048) chunk = 2048;
+  if (chunk < base) chunk = base;
   if (chunk > 0x3fffffff) chunk = 0x3fffffff;
   return static_cast<int>(chunk);
+}
+size_t ii_max_units(int n_items, int64_t nnz) {
+  return static_cast<size_t>(n_items) + static_cast<size_t>(nnz / ii_chunk(n_items, nnz)) + 1;
 }
 int ii_max_hot(int n_items, int64_t nnz) {
   const long long m = nnz / ii_chunk(n_items, nnz) + 1;
@@ -539,6 +652,8 @@ size_t item_item_workspace_bytes(int64_t n_users, int n_items, int64_t nnz) {
   b += align_up(static_cast<size_t>(n_items + 1) * 4, 256);   // unit_off
   b += align_up(static_cast<size_t>(n_items) * 4, 256);       // hot_of
   b += align_up(static_cast<size_t>(nnz) * 8, 256);           // csc (user, rating)
+  b += align_up(static_cast<size_t>(nnz) * 4, 256);           // packed (item | rating << 24)
+  b += align_up(ii_max_units(n_items, nnz) * 16, 256);        // unit table
   b += 1024;                                                  // bucket counters, unit / hot counts, work counter
   if (n_items <= kSmemHistItems / 2) b += 2 * align_up(static_cast<size_t>(kSortCtas) * n_items * 4, 256);   // per-CTA histograms + square norms
   const int max_hot = ii_max_hot(n_items, nnz);
@@ -571,6 +686,8 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   int* unit_off = reinterpret_cast<int*>(take(static_cast<size_t>(n_items + 1) * 4));
   int* hot_of = reinterpret_cast<int*>(take(static_cast<size_t>(n_items) * 4));
   int2* csc = reinterpret_cast<int2*>(take(static_cast<size_t>(nnz) * 8));
+  uint32_t* packed = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(nnz) * 4));
+  int4* unit_tab = reinterpret_cast<int4*>(take(ii_max_units(n_items, nnz) * 16));
   int* counters = reinterpret_cast<int*>(take(1024));   // [0..63] bucket_cnt, [64..127] bucket_pos, [128] units, [129] hot items, [130] work counter,
                                                         // [131] integer-accumulator mode, [132] non-integral rating seen, [133] largest rating, [134] flags valid
   const bool smem_sort = n_items <= kSmemHistItems / 2;   // (count + square-norm histograms side by side)
@@ -619,24 +736,36 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   ii_bucket_count_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters);
   ii_bucket_scan_kernel<<<1, 32, 0, stream>>>(counters, counters + 64);
   ii_bucket_scatter_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters + 64, order);
-  ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, counters + 128);
+  ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, unit_tab, counters + 128);
   ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
-  launches += 5;
+  ii_pack_kernel<<<sms * 8, 256, 0, stream>>>(indices, values, nnz, counters + 128, packed);
+  launches += 6;
 
-  // ---- 3. accumulate + select.  Accumulator range: as many items as fit beside the per-warp merge stages
+  // ---- 3. accumulate + select.  Accumulator range: as many items as fit beside the survivor buffer and warp 0's merger;
+  // two CTAs per SM whenever the accumulator leaves room (config 3: 100,864 + 10,240 B per CTA)
   const int max_smem = 227 * 1024;
-  const int stage_bytes = kAccWarps * kCap * 8;
-  int range = (max_smem - stage_bytes - 1024) / 4;
+  const int side_bytes = (kSelBuf + kCap) * 8;
+  int range = (max_smem - side_bytes - 1024) / 4;
   if (range > n_items) range = n_items;
   range = (range + 31) / 32 * 32;
-  const size_t smem = static_cast<size_t>(range) * 4 + stage_bytes;
-  e = cudaFuncSetAttribute(ii_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
-  const int ctas_per_sm = smem <= 110 * 1024 ? 2 : 1;
-  const int grid = sms * ctas_per_sm;
-  ii_accumulate_kernel<<<grid, kAccThreads, smem, stream>>>(indptr, indices, values, col_ptr, csc, sq, order, unit_off,
-                                                          hot_of, counters + 128, n_items, range, chunk, k, max_hot, hot_rows, hot_done,
-                                                          counters + 130, out_scores, out_ids);
+  const size_t smem = static_cast<size_t>(range) * 4 + side_bytes;
+  const bool two = smem <= 112 * 1024;
+  static const int variant = [] { const char* v = getenv("BB_II_VARIANT"); return v ? atoi(v) : 0; }();
+#define BB_II_LAUNCH(T, MB)                                                                                                \
+  do {                                                                                                                     \
+    e = cudaFuncSetAttribute(ii_accumulate_kernel<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                             static_cast<int>(smem));                                                                      \
+    if (e != cudaSuccess) return e;                                                                                        \
+    ii_accumulate_kernel<T, MB><<<sms * (two ? 2 : 1), T, smem, stream>>>(                                                 \
+        indptr, indices, values, packed, col_ptr, csc, sq, unit_tab, counters + 128, n_items, range, chunk, k, max_hot,   \
+        hot_rows, hot_done, counters + 130, out_scores, out_ids);                                                          \
+  } while (0)
+  switch (variant) {
+    case 4: BB_II_LAUNCH(768, 2); break;
+    case 5: BB_II_LAUNCH(1024, 2); break;
+    default: BB_II_LAUNCH(512, 2); break;
+  }
+#undef BB_II_LAUNCH
   ++launches;
   if (n_launches != nullptr) *n_launches = launches;
   return cudaGetLastError();
