@@ -93,11 +93,22 @@ __global__ void ii_column_prefix_kernel(uint32_t* __restrict__ block_hist, const
   if (i >= n_items) return;
   uint32_t run = 0u;
   float s = 0.f;
-  for (int g = 0; g < kSortCtas; ++g) {
-    const uint32_t c = block_hist[static_cast<int64_t>(g) * n_items + i];
-    block_hist[static_cast<int64_t>(g) * n_items + i] = run;
-    run += c;
-    s += block_sq[static_cast<int64_t>(g) * n_items + i];
+  constexpr int kBatch = 8;                        // independent loads per round (the loop is latency bound)
+  for (int g0 = 0; g0 < kSortCtas; g0 += kBatch) {
+    uint32_t c[kBatch];
+    float q[kBatch];
+#pragma unroll
+    for (int x = 0; x < kBatch; ++x) {
+      const bool in = g0 + x < kSortCtas;
+      c[x] = in ? block_hist[static_cast<int64_t>(g0 + x) * n_items + i] : 0u;
+      q[x] = in ? block_sq[static_cast<int64_t>(g0 + x) * n_items + i] : 0.f;
+    }
+#pragma unroll
+    for (int x = 0; x < kBatch; ++x) {
+      if (g0 + x < kSortCtas) block_hist[static_cast<int64_t>(g0 + x) * n_items + i] = run;
+      run += c[x];
+      s += q[x];
+    }
   }
   col_cnt[i] = run;
   sq[i] = s > 0.f ? 1.f / sqrtf(s) : 0.f;         // 1 / the item's L2 norm (what the cosine multiplies by)
@@ -111,6 +122,7 @@ __global__ void ii_scan_kernel(const unsigned long long* __restrict__ cnt, int n
   const int per = (n + 1023) / 1024;
   const int lo = t * per, hi = min(n, lo + per);
   long long s = 0;
+#pragma unroll 8
   for (int i = lo; i < hi; ++i) s += static_cast<long long>(cnt[i]);
   part[t] = s;
   __syncthreads();
@@ -213,6 +225,7 @@ __global__ void ii_units_kernel(const unsigned long long* __restrict__ col_cnt, 
   const int per = (n + 1023) / 1024;
   const int lo = t * per, hi = min(n, lo + per);
   int su = 0, sh = 0;
+#pragma unroll 8
   for (int p = lo; p < hi; ++p) {
     const long long d = static_cast<long long>(col_cnt[order[p]]);
     const int units = d <= chunk ? 1 : static_cast<int>((d + chunk - 1) / chunk);
