@@ -63,13 +63,23 @@ ii_block_hist_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
   const int64_t e0 = __ldg(indptr + u0), e1 = __ldg(indptr + u1);
   bool odd = false;                                 // a rating that is not an integer in [0, 1024]
   float vmax = 0.f;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += kAccThreads) {
-    const int32_t c = __ldg(indices + e);
-    const float v = __ldg(values + e);
-    atomicAdd(hist + c, 1u);
-    atomicAdd(sqs + c, v * v);
-    odd |= !(v >= 0.f && v <= 1024.f && v == floorf(v));
-    vmax = fmaxf(vmax, v);
+  for (int64_t eb = e0 + threadIdx.x; eb < e1; eb += 4 * kAccThreads) {
+    int32_t c[4];
+    float v[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int64_t e = eb + x * kAccThreads;
+      c[x] = e < e1 ? __ldg(indices + e) : -1;
+      v[x] = e < e1 ? __ldg(values + e) : 0.f;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      if (c[x] < 0) continue;
+      atomicAdd(hist + c[x], 1u);
+      atomicAdd(sqs + c[x], v[x] * v[x]);
+      odd |= !(v[x] >= 0.f && v[x] <= 1024.f && v[x] == floorf(v[x]));
+      vmax = fmaxf(vmax, v[x]);
+    }
   }
   if (__any_sync(kFull, odd) && (threadIdx.x & 31) == 0) atomicOr(value_flags, 1);
   vmax = fmaxf(vmax, __shfl_xor_sync(kFull, vmax, 16));
@@ -114,36 +124,62 @@ __global__ void ii_column_prefix_kernel(uint32_t* __restrict__ block_hist, const
   sq[i] = s > 0.f ? 1.f / sqrtf(s) : 0.f;         // 1 / the item's L2 norm (what the cosine multiplies by)
 }
 
-// single-block exclusive scan (n_items is catalog sized; this is microseconds)
-__global__ void ii_scan_kernel(const unsigned long long* __restrict__ cnt, int n, long long* __restrict__ ptr,
-                               unsigned long long* __restrict__ cursor) {
-  __shared__ long long part[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int lo = t * per, hi = min(n, lo + per);
-  long long s = 0;
-#pragma unroll 8
-  for (int i = lo; i < hi; ++i) s += static_cast<long long>(cnt[i]);
-  part[t] = s;
-  __syncthreads();
-  if (t == 0) {
-    long long run = 0;
-    for (int i = 0; i < 1024; ++i) { const long long v = part[i]; part[i] = run; run += v; }
-    ptr[n] = run;
+// Exclusive scan over n elements by ONE block of 1024 threads: coalesced chunks of 1024, warp shuffles, a running
+// carry.  `load(i)` yields element i, `store(i, exclusive_prefix, value)` consumes it; returns the total (all threads).
+template <typename Load, typename Store>
+__device__ __forceinline__ long long block_scan_1024(int n, Load load, Store store) {
+  __shared__ long long scan_ws[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  long long carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + t;
+    const long long v = i < n ? load(i) : 0ll;
+    long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long y = __shfl_up_sync(kFull, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) scan_ws[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      long long y = scan_ws[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const long long z = __shfl_up_sync(kFull, y, d);
+        if (lane >= d) y += z;
+      }
+      scan_ws[lane] = y;
+    }
+    __syncthreads();
+    if (i < n) store(i, carry + (warp > 0 ? scan_ws[warp - 1] : 0ll) + x - v, v);
+    carry += scan_ws[31];
+    __syncthreads();
   }
-  __syncthreads();
-  long long run = part[t];
-  for (int i = lo; i < hi; ++i) {
-    ptr[i] = run;
-    if (cursor != nullptr) cursor[i] = static_cast<unsigned long long>(run);
-    run += static_cast<long long>(cnt[i]);
-  }
+  return carry;
 }
 
+// column pointers from the column counts (single block; n_items is catalog sized)
+__global__ void __launch_bounds__(1024)
+ii_scan_kernel(const unsigned long long* __restrict__ cnt, int n, long long* __restrict__ ptr, unsigned long long* __restrict__ cursor) {
+  const long long total = block_scan_1024(
+      n, [&](int i) { return static_cast<long long>(cnt[i]); },
+      [&](int i, long long off, long long) {
+        ptr[i] = off;
+        if (cursor != nullptr) cursor[i] = static_cast<unsigned long long>(off);
+      });
+  if (threadIdx.x == 0) ptr[n] = total;
+}
+
+// A warp takes 32 consecutive users: their rows are ONE contiguous element range of the CSR arrays, read coalesced,
+// lane per element; the owning user of element e is the number of non-empty rows that start at or before e (row-start
+// bitmap of the 32-element window, one redux.or) -- no per-rating search in indptr.  Also writes the packed rating
+// words (item | rating << 24) when ii_units_kernel found the ratings small integers.
 __global__ void __launch_bounds__(kAccThreads)
 ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
                         int64_t n_users, int64_t nnz, int n_items, const uint32_t* __restrict__ block_hist,
-                        const long long* __restrict__ col_ptr, int2* __restrict__ csc) {
+                        const long long* __restrict__ col_ptr, int2* __restrict__ csc, const int* __restrict__ counters,
+                        uint32_t* __restrict__ packed) {
   extern __shared__ __align__(16) unsigned char ii_smem[];
   uint32_t* cursor = reinterpret_cast<uint32_t*>(ii_smem);          // [n_items]: this CTA's next slot inside every column
   const uint32_t* mine = block_hist + static_cast<int64_t>(blockIdx.x) * n_items;
@@ -151,18 +187,44 @@ ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   __syncthreads();
   int64_t u0, u1;
   sort_user_range(indptr, n_users, nnz, blockIdx.x, u0, u1);
-  // one thread per rating; its user is found by a search in the CTA's slice of indptr (rows are ~20 long: a warp per
-  // user would leave a third of the lanes idle and chain two dependent loads per row)
-  const int64_t e0 = __ldg(indptr + u0), e1 = __ldg(indptr + u1);
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += kAccThreads) {
-    int64_t lo = u0, hi = u1;                       // largest u with indptr[u] <= e
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (__ldg(indptr + mid) <= e) lo = mid; else hi = mid;
+  const bool pack = counters[7] != 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t ub = u0 + warp * 32; ub < u1; ub += kAccThreads) {
+    const int64_t u = ub + lane;
+    int64_t p0 = 0;
+    int len = 0;
+    if (u < u1) {
+      p0 = __ldg(indptr + u);
+      len = static_cast<int>(__ldg(indptr + u + 1) - p0);
     }
-    const int32_t c = __ldg(indices + e);
-    const long long pos = __ldg(col_ptr + c) + atomicAdd(cursor + c, 1u);
-    csc[pos] = make_int2(static_cast<int32_t>(lo), __float_as_int(__ldg(values + e)));
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    const int excl = incl - len;
+    const int64_t base = __shfl_sync(kFull, p0, 0);                 // (lane 0 is a valid user: ub < u1)
+    const unsigned nonempty = __ballot_sync(kFull, len > 0);
+    const unsigned src = __fns(nonempty, 0, lane + 1);              // lane of the (lane+1)-th non-empty row
+    int rbase = 0;                                                  // non-empty rows that start before the window
+#pragma unroll 2
+    for (int e0 = 0; e0 < total; e0 += 32) {
+      const int d = excl - e0;
+      const unsigned starts = __reduce_or_sync(kFull, (len > 0 && d >= 0 && d < 32) ? (1u << d) : 0u);
+      const int rank = rbase + __popc(starts & (0xffffffffu >> (31 - lane)));
+      rbase += __popc(starts);
+      const int owner = static_cast<int>(__shfl_sync(kFull, src, (rank - 1) & 31));
+      const int e = e0 + lane;
+      if (e < total) {
+        const int32_t c = __ldg(indices + base + e);
+        const float v = __ldg(values + base + e);
+        const long long pos = __ldg(col_ptr + c) + atomicAdd(cursor + c, 1u);
+        csc[pos] = make_int2(static_cast<int32_t>(ub + owner), __float_as_int(v));
+        if (pack) packed[base + e] = static_cast<uint32_t>(c) | (static_cast<uint32_t>(v) << 24);
+      }
+    }
   }
 }
 
@@ -217,64 +279,40 @@ __global__ void ii_bucket_scatter_kernel(const unsigned long long* __restrict__ 
 // unit_off[p] = first unit of the p-th item of `order`; hot_of[item] = row of the item in the partial-row buffer
 // (-1 for single-unit items); unit_tab[u] = (item, chunk index, units of the item, hot row).  counters[0] = number of
 // units, counters[1] = number of hot items, counters[3] = integer accumulators, counters[7] = packed ratings.  Single block.
-__global__ void ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* __restrict__ order, int n,
-                                int chunk, int* __restrict__ unit_off, int* __restrict__ hot_of, int4* __restrict__ unit_tab,
-                                int* __restrict__ counters) {
-  __shared__ int part_u[1024], part_h[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int lo = t * per, hi = min(n, lo + per);
-  int su = 0, sh = 0;
-#pragma unroll 8
-  for (int p = lo; p < hi; ++p) {
-    const long long d = static_cast<long long>(col_cnt[order[p]]);
-    const int units = d <= chunk ? 1 : static_cast<int>((d + chunk - 1) / chunk);
-    su += units;
-    sh += units > 1;
-  }
-  part_u[t] = su;
-  part_h[t] = sh;
-  __syncthreads();
-  if (t == 0) {
-    int ru = 0, rh = 0;
-    for (int i = 0; i < 1024; ++i) {
-      const int u = part_u[i], h = part_h[i];
-      part_u[i] = ru; part_h[i] = rh;
-      ru += u; rh += h;
-    }
-    counters[0] = ru;
-    counters[1] = rh;
-    unit_off[n] = ru;
+__global__ void __launch_bounds__(1024)
+ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* __restrict__ order, int n, int chunk,
+                int* __restrict__ unit_off, int* __restrict__ hot_of, int4* __restrict__ unit_tab, int* __restrict__ counters) {
+  if (threadIdx.x == 0) {
     // integer accumulators are exact while vmax^2 * (largest degree) stays below 2^31
     // (order[0] lies in the top floor(log2(degree + 1)) bucket: no degree exceeds twice its own + 1)
     const long long dmax = n > 0 ? 2 * (static_cast<long long>(col_cnt[order[0]]) + 1) : 1;
     const long long vm = counters[5];
     counters[3] = (counters[4] == 0 && counters[6] == 1 && vm * vm * dmax < (1ll << 31)) ? 1 : 0;
-    // packed ratings: (item | rating << 24) in one word per rating (ii_pack_kernel)
+    // packed ratings: (item | rating << 24) in one word per rating (written by ii_block_scatter_kernel)
     counters[7] = (counters[3] != 0 && vm < 256 && n <= (1 << 24)) ? 1 : 0;
   }
-  __syncthreads();
-  int ru = part_u[t], rh = part_h[t];
-  for (int p = lo; p < hi; ++p) {
-    const int item = order[p];
-    const long long d = static_cast<long long>(col_cnt[item]);
-    const int units = d <= chunk ? 1 : static_cast<int>((d + chunk - 1) / chunk);
-    unit_off[p] = ru;
-    const int hot = units > 1 ? rh : -1;
-    hot_of[item] = hot;
-    for (int c = 0; c < units; ++c) unit_tab[ru + c] = make_int4(item, c, units, hot);
-    ru += units;
-    rh += units > 1;
+  // one scan carries both counts: units in the low word, hot items (more than one unit) in the high word
+  const long long total = block_scan_1024(
+      n,
+      [&](int p) {
+        const long long d = static_cast<long long>(col_cnt[order[p]]);
+        const long long units = d <= chunk ? 1 : (d + chunk - 1) / chunk;
+        return units | (static_cast<long long>(units > 1) << 32);
+      },
+      [&](int p, long long off, long long v) {
+        const int item = order[p];
+        const int units = static_cast<int>(v & 0xffffffffll);
+        const int ru = static_cast<int>(off & 0xffffffffll), rh = static_cast<int>(off >> 32);
+        const int hot = units > 1 ? rh : -1;
+        unit_off[p] = ru;
+        hot_of[item] = hot;
+        for (int c = 0; c < units; ++c) unit_tab[ru + c] = make_int4(item, c, units, hot);
+      });
+  if (threadIdx.x == 0) {
+    counters[0] = static_cast<int>(total & 0xffffffffll);
+    counters[1] = static_cast<int>(total >> 32);
+    unit_off[n] = counters[0];
   }
-}
-
-// small non-negative integer ratings: one word per rating halves the accumulate pass's row reads (and the packed
-// matrix of config 3, 78 MB, stays in L2)
-__global__ void ii_pack_kernel(const int32_t* __restrict__ indices, const float* __restrict__ values, int64_t nnz,
-                               const int* __restrict__ counters, uint32_t* __restrict__ packed) {
-  if (counters[7] == 0) return;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz; e += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    packed[e] = static_cast<uint32_t>(__ldg(indices + e)) | (static_cast<uint32_t>(__ldg(values + e)) << 24);
 }
 
 __global__ void ii_zero_hot_kernel(float* __restrict__ hot_rows, int* __restrict__ hot_done, const int* __restrict__ counters,
@@ -354,67 +392,63 @@ struct IIMerger {          // per-warp running top-128 (same scheme as the scan 
 //           repeats (only the <= k threads whose best reaches T hold survivors: a repeat is the rare case).
 constexpr int kSelBuf = 1024;                      // keys of the survivor buffer (aliases the per-warp sorted bests)
 
-__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const uint64_t o = __shfl_xor_sync(kFull, v, d);
-    v = o > v ? o : v;
-  }
-  return v;
-}
-
 struct IISelShared {       // static shared state of the selection
-  unsigned long long thr;  // T as a key
+  float thr_c;             // T: at least k items of the row score >= T
   int cnt;                 // survivors appended in this round
   int more;                // some survivors did not fit: repeat pass C
 };
 
 template <int kThreads, bool kInt>
 __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i, float inv_i, const float* __restrict__ inv_norm, int k,
-                                               uint64_t* buf, IISelShared* sh, IIMerger& mg, uint64_t& thr, int tid) {
+                                               uint64_t* buf, IISelShared* sh, IIMerger& mg, float& thr_c, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
   const int n4 = (n + 3) >> 2;                     // (entries in [n, range) are never written: they stay zero)
   uint4* acc4 = reinterpret_cast<uint4*>(acc);
   // pass A
   float best_c = 0.f;
-  int best_j = 0;
   for (int q = tid; q < n4; q += kThreads) {
     const uint4 w = acc4[q];
     if ((w.x | w.y | w.z | w.w) != 0u) {
+      const float4 inv4 = __ldg(reinterpret_cast<const float4*>(inv_norm + j0) + q);   // (j0 is a multiple of 32; padded allocation)
       const unsigned wu[4] = {w.x, w.y, w.z, w.w};
+      const float iv[4] = {inv4.x, inv4.y, inv4.z, inv4.w};
       float c[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int j = j0 + q * 4 + u;
-        c[u] = 0.f;
-        if (wu[u] != 0u) {
-          const float g = kInt ? static_cast<float>(wu[u]) : __uint_as_float(wu[u]);
-          if (g > 0.f && j != i) c[u] = g * (inv_i * __ldg(inv_norm + j));
-          if (c[u] > best_c) { best_c = c[u]; best_j = j; }       // ascending j: ties keep the lower id
-        }
+        const float g = kInt ? static_cast<float>(wu[u]) : __uint_as_float(wu[u]);
+        c[u] = (g > 0.f && j0 + q * 4 + u != i) ? g * (inv_i * iv[u]) : 0.f;
+        best_c = fmaxf(best_c, c[u]);
       }
       reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
     }
   }
-  uint64_t v[1] = {best_c > 0.f ? make_key(best_c, static_cast<uint32_t>(best_j)) : 0ull};
-  warp_sort_desc<1>(v, lane);
-  buf[warp * 32 + lane] = v[0];
+  // bound: T = k-th largest thread best (scores of k distinct items).  Positive floats order like their bit patterns.
+  unsigned v[1] = {__float_as_uint(best_c)};
+  warp_sort_desc<1, unsigned>(v, lane);
+  unsigned* tops = reinterpret_cast<unsigned*>(buf);                 // [kWarps][32], dead before pass C fills buf
+  tops[warp * 32 + lane] = v[0];
   __syncthreads();
   if (warp == 0) {
-    int ptr = 0;
-    uint64_t head = lane < kWarps ? buf[lane * 32] : 0ull;
-    uint64_t m = 0ull;
-    for (int it = 0; it < k; ++it) {
-      m = warp_max_u64(head);
-      if (m == 0ull) break;
-      if (head == m) { ++ptr; head = ptr < 32 ? buf[lane * 32 + ptr] : 0ull; }
+    int ptr = 0, popped = 0;
+    unsigned head = lane < kWarps ? tops[lane * 32] : 0u;
+    unsigned m = 0u;
+    while (popped < k) {
+      m = __reduce_max_sync(kFull, head);
+      if (m == 0u) break;
+      const bool hit = head == m;                  // equal scores pop together: at least `popped` items reach m
+      popped += __popc(__ballot_sync(kFull, hit));
+      if (hit) { ++ptr; head = ptr < 32 ? tops[lane * 32 + ptr] : 0u; }
     }
-    if (lane == 0) { sh->thr = m > thr ? m : thr; sh->cnt = 0; sh->more = 0; }
+    if (lane == 0) {
+      const float t_new = popped >= k ? __uint_as_float(m) : 0.f;
+      sh->thr_c = fmaxf(t_new, thr_c);
+      sh->cnt = 0;
+      sh->more = 0;
+    }
   }
   __syncthreads();
-  thr = sh->thr;
-  const float thr_c = thr != 0ull ? key_score(thr) : 0.f;
+  thr_c = sh->thr_c;
   // pass C
   while (true) {
     for (int q = tid; q < n4; q += kThreads) {
@@ -424,13 +458,8 @@ __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i,
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (c[u] >= thr_c && c[u] > 0.f) {
-            const uint64_t key = make_key(c[u], static_cast<uint32_t>(j0 + q * 4 + u));
-            if (key >= thr) {
-              const int pos = atomicAdd(&sh->cnt, 1);
-              if (pos < kSelBuf) { buf[pos] = key; c[u] = 0.f; }
-            } else {
-              c[u] = 0.f;
-            }
+            const int pos = atomicAdd(&sh->cnt, 1);
+            if (pos < kSelBuf) { buf[pos] = make_key(c[u], static_cast<uint32_t>(j0 + q * 4 + u)); c[u] = 0.f; }
           } else {
             c[u] = 0.f;
           }
@@ -527,7 +556,7 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
     const bool single = n_item_units == 1;
     const float inv_i = __ldg(inv_norm + i);
     IIMerger mg;
-    uint64_t thr = 0ull;
+    float thr_c = 0.f;
     if (single && warp == 0) mg.init(mstage, lane);
 
     for (int j0 = 0; j0 < n_items; j0 += range) {
@@ -556,29 +585,41 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
         const int total = __shfl_sync(kFull, incl, 31);
         const int64_t abase = cur.p0 - (incl - cur.len);       // element e of the flattened range lives at abase + e
         int rbase = 0;                                         // rows that end before the window
-#pragma unroll 2
-        for (int e0 = 0; e0 < total; e0 += 32) {
-          const int d = incl - e0;
-          const unsigned ends = __reduce_or_sync(kFull, (d >= 0 && d < 32) ? (1u << d) : 0u);
-          const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
-          rbase += __popc(ends);
-          const int e = e0 + lane;
-          const int64_t q = __shfl_sync(kFull, abase, r) + e;
-          const unsigned rr = __shfl_sync(kFull, cur.r, r);
-          if (e < total) {
-            if (use_packed) {
-              const uint32_t w = __ldg(packed + q);
-              const int j = static_cast<int>(w & 0xffffffu);
-              if (j >= j0 && j < j1) atomicAdd(reinterpret_cast<unsigned*>(acc) + (j - j0), rr * (w >> 24));
-            } else {
-              const int32_t j = __ldg(indices + q);
-              const float v = __ldg(values + q);
-              if (j >= j0 && j < j1) {
-                // integral ratings (the usual 1..5 stars): native integer shared-memory atomics; a float atomicAdd on
-                // shared memory is a compare-and-swap loop that spins on popular items
-                if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (j - j0), rr * static_cast<unsigned>(v));
-                else atomicAdd(acc + (j - j0), __uint_as_float(rr) * v);
+        // four windows per round: the round's row reads are issued before the first shared-memory atomic needs one
+        for (int e0 = 0; e0 < total; e0 += 128) {
+          int jj[4];
+          unsigned vv[4], rr[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int w0 = e0 + 32 * x;
+            const int d = incl - w0;
+            const unsigned ends = __reduce_or_sync(kFull, (d >= 0 && d < 32) ? (1u << d) : 0u);
+            const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
+            rbase += __popc(ends);
+            const int e = w0 + lane;
+            const int64_t q = __shfl_sync(kFull, abase, r & 31) + e;
+            rr[x] = __shfl_sync(kFull, cur.r, r & 31);
+            jj[x] = -1;
+            vv[x] = 0u;
+            if (e < total) {
+              if (use_packed) {
+                const uint32_t w = __ldg(packed + q);
+                jj[x] = static_cast<int>(w & 0xffffffu);
+                vv[x] = w >> 24;
+              } else {
+                jj[x] = __ldg(indices + q);
+                vv[x] = __float_as_uint(__ldg(values + q));
               }
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            if (jj[x] >= j0 && jj[x] < j1) {
+              // integral ratings (the usual 1..5 stars): native integer shared-memory atomics; a float atomicAdd on
+              // shared memory is a compare-and-swap loop that spins on popular items
+              if (use_packed) atomicAdd(reinterpret_cast<unsigned*>(acc) + (jj[x] - j0), rr[x] * vv[x]);
+              else if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (jj[x] - j0), rr[x] * static_cast<unsigned>(__uint_as_float(vv[x])));
+              else atomicAdd(acc + (jj[x] - j0), __uint_as_float(rr[x]) * __uint_as_float(vv[x]));
             }
           }
         }
@@ -586,8 +627,8 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
       }
       __syncthreads();
       if (single) {
-        if (int_mode) ii_select_smem<kThreads, true>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr, tid);
-        else ii_select_smem<kThreads, false>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr, tid);
+        if (int_mode) ii_select_smem<kThreads, true>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr_c, tid);
+        else ii_select_smem<kThreads, false>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr_c, tid);
       } else {
         float* row = hot_rows + static_cast<int64_t>(hot) * n_items + j0;
         const bool add = hot >= 0 && hot < max_hot;
@@ -621,7 +662,7 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
           const float* row = hot_rows + static_cast<int64_t>(hot) * n_items + j0;
           for (int j = tid; j < j1 - j0; j += kThreads) acc[j] = __ldcg(row + j);
           __syncthreads();
-          ii_select_smem<kThreads, false>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr, tid);
+          ii_select_smem<kThreads, false>(acc, j1 - j0, j0, i, inv_i, inv_norm, k, buf, &s_sel, mg, thr_c, tid);
         }
         if (warp == 0) {
           mg.flush();
@@ -715,7 +756,16 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   cudaMemsetAsync(sq, 0, static_cast<size_t>(n_items) * 4, stream);
   cudaMemsetAsync(counters, 0, 1024, stream);
   int launches = 0;
-  // ---- 1. CSC
+  // ---- 1. column counts, norms, column pointers; 2. work units, hot items first; then the CSC scatter (which needs the
+  // "ratings are small integers" verdict of the units kernel to write the packed rating words)
+  auto plan_units = [&]() {
+    ii_bucket_count_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters);
+    ii_bucket_scan_kernel<<<1, 32, 0, stream>>>(counters, counters + 64);
+    ii_bucket_scatter_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters + 64, order);
+    ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, unit_tab, counters + 128);
+    ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
+    launches += 5;
+  };
   if (smem_sort) {
     const size_t hist_smem = static_cast<size_t>(n_items) * 8;
     if (hist_smem > 48 * 1024) {
@@ -728,8 +778,9 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
                                                                        counters + 128 + 4);
     ii_column_prefix_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(block_hist, block_sq, n_items, col_cnt, sq);
     ii_scan_kernel<<<1, 1024, 0, stream>>>(col_cnt, n_items, col_ptr, nullptr);
+    plan_units();
     ii_block_scatter_kernel<<<kSortCtas, kAccThreads, hist_smem, stream>>>(indptr, indices, values, n_users, nnz, n_items, block_hist,
-                                                                          col_ptr, csc);
+                                                                          col_ptr, csc, counters + 128, packed);
     launches += 4;
   } else {
     if (nnz > 0) {
@@ -744,15 +795,8 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
                                                                                         cursor, csc);
       ++launches;
     }
+    plan_units();
   }
-  // ---- 2. work units, hot items first
-  ii_bucket_count_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters);
-  ii_bucket_scan_kernel<<<1, 32, 0, stream>>>(counters, counters + 64);
-  ii_bucket_scatter_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters + 64, order);
-  ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, unit_tab, counters + 128);
-  ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
-  ii_pack_kernel<<<sms * 8, 256, 0, stream>>>(indices, values, nnz, counters + 128, packed);
-  launches += 6;
 
   // ---- 3. accumulate + select.  Accumulator range: as many items as fit beside the survivor buffer and warp 0's merger;
   // two CTAs per SM whenever the accumulator leaves room (config 3: 100,864 + 10,240 B per CTA)

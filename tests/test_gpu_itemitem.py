@@ -83,3 +83,22 @@ def test_wide_item_sets_take_the_fallback_sort_and_two_ranges(bb):
     rows = np.concatenate([order[:6], order[3000:3004], order[-4:]]).astype(int)
     _check_rows(indptr, indices, data, n_items, k, s, i, rows)
     eng.close()
+
+
+def test_users_without_ratings_and_unrated_items(bb):
+    """Empty CSR rows between rated ones (the scatter finds a rating's user from row-start bitmaps: empty rows must not
+    shift the owners), items nobody rated, fewer positive neighbours than k (zero-similarity fill)."""
+    rng = np.random.default_rng(11)
+    n_items, n_users, k = 700, 5000, 12
+    lens = rng.integers(0, 9, size=n_users)
+    lens[rng.random(n_users) < 0.4] = 0                        # 40% of the users rated nothing
+    lens[:40] = 0
+    lens[-3:] = 0
+    indptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(600, size=l, replace=False)) for l in lens if l] or [np.zeros(0, int)]).astype(np.int32)
+    data = rng.integers(1, 6, size=indices.shape[0]).astype(np.float32)      # items 600..699 stay unrated
+    eng = bb.ScoringEngine(1, 1, 0)
+    s, i = eng.item_item_topk(indptr, indices, data, n_items, k)
+    _check_rows(indptr, indices, data, n_items, k, s, i, np.arange(0, n_items, 7))
+    eng.close()
