@@ -631,7 +631,7 @@ def run_item_item(args):
             "roofline": {"bound": "hbm", "kernel": "ii_accumulate_kernel", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "macs": macs, "gmacs_per_s": macs / (ms * 1e-3) / 1e9,
-                         "note": "achieved = (8 B per rating + indptr + N*k*8 B out) / whole item-item pass; the pass is bound by shared-memory atomics, not by these bytes"}}
+                         "note": "achieved = (8 B per rating + indptr + N*k*8 B out) / whole item-item pass; the pass is latency / issue bound (row gathers from L2 + two dense selection passes per item in shared memory), not bound by these bytes -- profiles/r2_item_item_ncu.md"}}
     emit(line)
     D.close()
 

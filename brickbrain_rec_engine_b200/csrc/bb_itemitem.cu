@@ -174,16 +174,19 @@ ii_scan_kernel(const unsigned long long* __restrict__ cnt, int n, long long* __r
 // A warp takes 32 consecutive users: their rows are ONE contiguous element range of the CSR arrays, read coalesced,
 // lane per element; the owning user of element e is the number of non-empty rows that start at or before e (row-start
 // bitmap of the 32-element window, one redux.or) -- no per-rating search in indptr.  Also writes the packed rating
-// words (item | rating << 24) when ii_units_kernel found the ratings small integers.
+// words (item | rating << 24) when ii_units_kernel found the ratings small integers.  What is left (0.45 ms at config 3)
+// is the price of 19.6M random 8-byte stores: half of the 32-byte sectors leave L2 partially written and come back for a
+// read-modify-write (ncu: 250 MB of fills, 236 MB of repeated write-backs); writing the output in L2-sized column slices
+// (re-reading the ratings per slice) did not change the time, so a write-combining radix partition would be the next step.
 __global__ void __launch_bounds__(kAccThreads)
 ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
                         int64_t n_users, int64_t nnz, int n_items, const uint32_t* __restrict__ block_hist,
                         const long long* __restrict__ col_ptr, int2* __restrict__ csc, const int* __restrict__ counters,
                         uint32_t* __restrict__ packed) {
   extern __shared__ __align__(16) unsigned char ii_smem[];
-  uint32_t* cursor = reinterpret_cast<uint32_t*>(ii_smem);          // [n_items]: this CTA's next slot inside every column
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(ii_smem);          // [n_items]: this CTA's next ABSOLUTE slot of every column (nnz < 2^32)
   const uint32_t* mine = block_hist + static_cast<int64_t>(blockIdx.x) * n_items;
-  for (int i = threadIdx.x; i < n_items; i += kAccThreads) cursor[i] = mine[i];
+  for (int i = threadIdx.x; i < n_items; i += kAccThreads) cursor[i] = static_cast<uint32_t>(col_ptr[i]) + mine[i];
   __syncthreads();
   int64_t u0, u1;
   sort_user_range(indptr, n_users, nnz, blockIdx.x, u0, u1);
@@ -209,20 +212,28 @@ ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
     const unsigned nonempty = __ballot_sync(kFull, len > 0);
     const unsigned src = __fns(nonempty, 0, lane + 1);              // lane of the (lane+1)-th non-empty row
     int rbase = 0;                                                  // non-empty rows that start before the window
-#pragma unroll 2
-    for (int e0 = 0; e0 < total; e0 += 32) {
-      const int d = excl - e0;
-      const unsigned starts = __reduce_or_sync(kFull, (len > 0 && d >= 0 && d < 32) ? (1u << d) : 0u);
-      const int rank = rbase + __popc(starts & (0xffffffffu >> (31 - lane)));
-      rbase += __popc(starts);
-      const int owner = static_cast<int>(__shfl_sync(kFull, src, (rank - 1) & 31));
-      const int e = e0 + lane;
-      if (e < total) {
-        const int32_t c = __ldg(indices + base + e);
-        const float v = __ldg(values + base + e);
-        const long long pos = __ldg(col_ptr + c) + atomicAdd(cursor + c, 1u);
-        csc[pos] = make_int2(static_cast<int32_t>(ub + owner), __float_as_int(v));
-        if (pack) packed[base + e] = static_cast<uint32_t>(c) | (static_cast<uint32_t>(v) << 24);
+    for (int e0 = 0; e0 < total; e0 += 128) {                       // four windows of rating reads in flight
+      int32_t c[4];
+      float v[4];
+      int owner[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int w0 = e0 + 32 * x;
+        const int d = excl - w0;
+        const unsigned starts = __reduce_or_sync(kFull, (len > 0 && d >= 0 && d < 32) ? (1u << d) : 0u);
+        const int rank = rbase + __popc(starts & (0xffffffffu >> (31 - lane)));
+        rbase += __popc(starts);
+        owner[x] = static_cast<int>(__shfl_sync(kFull, src, (rank - 1) & 31));
+        const int e = w0 + lane;
+        c[x] = e < total ? __ldcs(indices + base + e) : -1;
+        v[x] = e < total ? __ldcs(values + base + e) : 0.f;
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        if (c[x] < 0) continue;
+        const uint32_t pos = atomicAdd(cursor + c[x], 1u);
+        csc[pos] = make_int2(static_cast<int32_t>(ub + owner[x]), __float_as_int(v[x]));
+        if (pack) packed[base + e0 + 32 * x + lane] = static_cast<uint32_t>(c[x]) | (static_cast<uint32_t>(v[x]) << 24);
       }
     }
   }
@@ -386,10 +397,11 @@ struct IIMerger {          // per-warp running top-128 (same scheme as the scan 
 // for 405M multiply-adds at config 3, i.e. the pass was bound by the sort networks.  Now:
 //   pass A  every thread turns its entries into cosines in place (four per shared-memory read) and keeps its best;
 //   bound   T = k-th largest of the thread bests (each is the score of a distinct item, so at least k items reach T):
-//           per-warp 32-key sorts, then warp 0 pops k times from the heads of the sorted lists;
+//           per-warp 32-key sorts, then warp 0 pops from the heads of the sorted lists (one redux.max per pop);
 //   pass C  entries >= T go to a small CTA buffer that warp 0 drains into ONE merger; everything that was handled is
 //           zeroed (the accumulator is clean for the next unit), an entry that found the buffer full stays and the pass
-//           repeats (only the <= k threads whose best reaches T hold survivors: a repeat is the rare case).
+//           repeats (rare: T admits about k entries).
+// (Deriving T from a sixth of the row and computing the cosines in pass C instead was slower: 3.08 vs 2.81 ms.)
 constexpr int kSelBuf = 1024;                      // keys of the survivor buffer (aliases the per-warp sorted bests)
 
 struct IISelShared {       // static shared state of the selection
@@ -404,13 +416,14 @@ __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i,
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kThreads / 32;
   const int n4 = (n + 3) >> 2;                     // (entries in [n, range) are never written: they stay zero)
-  uint4* acc4 = reinterpret_cast<uint4*>(acc);
+  const uint4* acc4 = reinterpret_cast<const uint4*>(acc);
+  const float4* inv4p = reinterpret_cast<const float4*>(inv_norm + j0);     // (j0 is a multiple of 32; padded allocation)
   // pass A
   float best_c = 0.f;
   for (int q = tid; q < n4; q += kThreads) {
     const uint4 w = acc4[q];
     if ((w.x | w.y | w.z | w.w) != 0u) {
-      const float4 inv4 = __ldg(reinterpret_cast<const float4*>(inv_norm + j0) + q);   // (j0 is a multiple of 32; padded allocation)
+      const float4 inv4 = __ldg(inv4p + q);
       const unsigned wu[4] = {w.x, w.y, w.z, w.w};
       const float iv[4] = {inv4.x, inv4.y, inv4.z, inv4.w};
       float c[4];
@@ -418,8 +431,8 @@ __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i,
       for (int u = 0; u < 4; ++u) {
         const float g = kInt ? static_cast<float>(wu[u]) : __uint_as_float(wu[u]);
         c[u] = (g > 0.f && j0 + q * 4 + u != i) ? g * (inv_i * iv[u]) : 0.f;
-        best_c = fmaxf(best_c, c[u]);
       }
+      best_c = fmaxf(fmaxf(fmaxf(best_c, c[0]), fmaxf(c[1], c[2])), c[3]);
       reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
     }
   }
@@ -566,7 +579,7 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
         IIRaters f = {0, 0, 0u};
         const long long mine = (x0 + lane) * kWarps + warp;
         if (mine < n_raters) {
-          const int2 ur = __ldg(csc + e_begin + mine);
+          const int2 ur = __ldcs(csc + e_begin + mine);        // read once: evict first, the packed rows should stay in L2
           f.r = int_mode ? static_cast<unsigned>(__int_as_float(ur.y)) : static_cast<unsigned>(ur.y);
           f.p0 = __ldg(indptr + ur.x);
           f.len = static_cast<int>(__ldg(indptr + ur.x + 1) - f.p0);
@@ -585,41 +598,60 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
         const int total = __shfl_sync(kFull, incl, 31);
         const int64_t abase = cur.p0 - (incl - cur.len);       // element e of the flattened range lives at abase + e
         int rbase = 0;                                         // rows that end before the window
-        // four windows per round: the round's row reads are issued before the first shared-memory atomic needs one
-        for (int e0 = 0; e0 < total; e0 += 128) {
-          int jj[4];
-          unsigned vv[4], rr[4];
+        // several windows per round: the round's row reads are issued before the first shared-memory atomic needs one
+        // (packed words: eight windows, 1 KB of row reads in flight per warp)
+        if (use_packed) {
+          for (int e0 = 0; e0 < total; e0 += 256) {
+            uint32_t ww[8];
+            unsigned rr[8];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const int w0 = e0 + 32 * x;
-            const int d = incl - w0;
-            const unsigned ends = __reduce_or_sync(kFull, (d >= 0 && d < 32) ? (1u << d) : 0u);
-            const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
-            rbase += __popc(ends);
-            const int e = w0 + lane;
-            const int64_t q = __shfl_sync(kFull, abase, r & 31) + e;
-            rr[x] = __shfl_sync(kFull, cur.r, r & 31);
-            jj[x] = -1;
-            vv[x] = 0u;
-            if (e < total) {
-              if (use_packed) {
-                const uint32_t w = __ldg(packed + q);
-                jj[x] = static_cast<int>(w & 0xffffffu);
-                vv[x] = w >> 24;
-              } else {
+            for (int x = 0; x < 8; ++x) {
+              const int w0 = e0 + 32 * x;
+              const int d = incl - w0;
+              const unsigned ends = __reduce_or_sync(kFull, (d >= 0 && d < 32) ? (1u << d) : 0u);
+              const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
+              rbase += __popc(ends);
+              const int e = w0 + lane;
+              const int64_t q = __shfl_sync(kFull, abase, r & 31) + e;
+              rr[x] = __shfl_sync(kFull, cur.r, r & 31);
+              ww[x] = e < total ? __ldg(packed + q) : 0u;                 // (rating 0: adds nothing, skipped below)
+            }
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+              const int j = static_cast<int>(ww[x] & 0xffffffu) - j0;
+              if (static_cast<unsigned>(j) < static_cast<unsigned>(j1 - j0) && (ww[x] >> 24) != 0u)
+                atomicAdd(reinterpret_cast<unsigned*>(acc) + j, rr[x] * (ww[x] >> 24));
+            }
+          }
+        } else {
+          for (int e0 = 0; e0 < total; e0 += 128) {
+            int jj[4];
+            unsigned vv[4], rr[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const int w0 = e0 + 32 * x;
+              const int d = incl - w0;
+              const unsigned ends = __reduce_or_sync(kFull, (d >= 0 && d < 32) ? (1u << d) : 0u);
+              const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
+              rbase += __popc(ends);
+              const int e = w0 + lane;
+              const int64_t q = __shfl_sync(kFull, abase, r & 31) + e;
+              rr[x] = __shfl_sync(kFull, cur.r, r & 31);
+              jj[x] = -1;
+              vv[x] = 0u;
+              if (e < total) {
                 jj[x] = __ldg(indices + q);
                 vv[x] = __float_as_uint(__ldg(values + q));
               }
             }
-          }
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            if (jj[x] >= j0 && jj[x] < j1) {
-              // integral ratings (the usual 1..5 stars): native integer shared-memory atomics; a float atomicAdd on
-              // shared memory is a compare-and-swap loop that spins on popular items
-              if (use_packed) atomicAdd(reinterpret_cast<unsigned*>(acc) + (jj[x] - j0), rr[x] * vv[x]);
-              else if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (jj[x] - j0), rr[x] * static_cast<unsigned>(__uint_as_float(vv[x])));
-              else atomicAdd(acc + (jj[x] - j0), __uint_as_float(rr[x]) * __uint_as_float(vv[x]));
+            for (int x = 0; x < 4; ++x) {
+              if (jj[x] >= j0 && jj[x] < j1) {
+                // integral ratings too large to pack: native integer shared-memory atomics; a float atomicAdd on
+                // shared memory is a compare-and-swap loop that spins on popular items
+                if (int_mode) atomicAdd(reinterpret_cast<unsigned*>(acc) + (jj[x] - j0), rr[x] * static_cast<unsigned>(__uint_as_float(vv[x])));
+                else atomicAdd(acc + (jj[x] - j0), __uint_as_float(rr[x]) * __uint_as_float(vv[x]));
+              }
             }
           }
         }
@@ -674,10 +706,10 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
   }
 }
 
-// raters per work unit: 8192 (BB_II_CHUNK), raised so that the partial-row buffer (<= nnz / chunk hot items x n_items floats) stays
+// raters per work unit: 16384 (BB_II_CHUNK), raised so that the partial-row buffer (<= nnz / chunk hot items x n_items floats) stays
 // within 1 GiB
 int ii_chunk(int n_items, int64_t nnz) {
-  static const long long base = [] { const char* v = getenv("BB_II_CHUNK"); const long long c = v ? atoll(v) : 0; return c >= 256 ? c : 8192; }();
+  static const long long base = [] { const char* v = getenv("BB_II_CHUNK"); const long long c = v ? atoll(v) : 0; return c >= 256 ? c : 16384; }();
   long long chunk = base;
   const long long budget_rows = (1ll << 30) / (static_cast<long long>(n_items) * 4 + 1);
   if (budget_rows > 0 && nnz / chunk > budget_rows) chunk = (nnz + budget_rows - 1) / budget_rows;
@@ -709,7 +741,7 @@ size_t item_item_workspace_bytes(int64_t n_users, int n_items, int64_t nnz) {
   b += align_up(static_cast<size_t>(nnz) * 4, 256);           // packed (item | rating << 24)
   b += align_up(ii_max_units(n_items, nnz) * 16, 256);        // unit table
   b += 1024;                                                  // bucket counters, unit / hot counts, work counter
-  if (n_items <= kSmemHistItems / 2) b += 2 * align_up(static_cast<size_t>(kSortCtas) * n_items * 4, 256);   // per-CTA histograms + square norms
+  if (n_items <= kSmemHistItems / 2 && nnz < 0xffffffffll) b += 2 * align_up(static_cast<size_t>(kSortCtas) * n_items * 4, 256);   // per-CTA histograms + square norms
   const int max_hot = ii_max_hot(n_items, nnz);
   b += align_up(static_cast<size_t>(max_hot) * n_items * 4, 256);   // partial rows of hot items
   b += align_up(static_cast<size_t>(max_hot) * 4, 256);             // hot_done
@@ -744,7 +776,7 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   int4* unit_tab = reinterpret_cast<int4*>(take(ii_max_units(n_items, nnz) * 16));
   int* counters = reinterpret_cast<int*>(take(1024));   // [0..63] bucket_cnt, [64..127] bucket_pos, [128] units, [129] hot items, [130] work counter,
                                                         // [131] integer-accumulator mode, [132] non-integral rating seen, [133] largest rating, [134] flags valid
-  const bool smem_sort = n_items <= kSmemHistItems / 2;   // (count + square-norm histograms side by side)
+  const bool smem_sort = n_items <= kSmemHistItems / 2 && nnz < 0xffffffffll;   // (count + square-norm histograms side by side; 32-bit cursors)
   uint32_t* block_hist = smem_sort ? reinterpret_cast<uint32_t*>(take(static_cast<size_t>(kSortCtas) * n_items * 4)) : nullptr;
   float* block_sq = smem_sort ? reinterpret_cast<float*>(take(static_cast<size_t>(kSortCtas) * n_items * 4)) : nullptr;
   const int chunk = ii_chunk(n_items, nnz);
@@ -807,21 +839,18 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   range = (range + 31) / 32 * 32;
   const size_t smem = static_cast<size_t>(range) * 4 + side_bytes;
   const bool two = smem <= 112 * 1024;
-  static const int variant = [] { const char* v = getenv("BB_II_VARIANT"); return v ? atoi(v) : 0; }();
 #define BB_II_LAUNCH(T, MB)                                                                                                \
   do {                                                                                                                     \
     e = cudaFuncSetAttribute(ii_accumulate_kernel<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                              static_cast<int>(smem));                                                                      \
     if (e != cudaSuccess) return e;                                                                                        \
-    ii_accumulate_kernel<T, MB><<<sms * (two ? 2 : 1), T, smem, stream>>>(                                                 \
+    ii_accumulate_kernel<T, MB><<<sms * MB, T, smem, stream>>>(                                                            \
         indptr, indices, values, packed, col_ptr, csc, sq, unit_tab, counters + 128, n_items, range, chunk, k, max_hot,   \
         hot_rows, hot_done, counters + 130, out_scores, out_ids);                                                          \
   } while (0)
-  switch (variant) {
-    case 4: BB_II_LAUNCH(768, 2); break;
-    case 5: BB_II_LAUNCH(1024, 2); break;
-    default: BB_II_LAUNCH(512, 2); break;
-  }
+  // (measured at config 3: 2 x 512 threads 2.81 ms, 2 x 768 3.7 ms, 2 x 1024 -- 32 registers, spills -- slower still)
+  if (two) BB_II_LAUNCH(512, 2);
+  else BB_II_LAUNCH(1024, 1);
 #undef BB_II_LAUNCH
   ++launches;
   if (n_launches != nullptr) *n_launches = launches;

@@ -56,7 +56,7 @@ if __name__ == "__main__":
     ap.add_argument("--n-items", type=int, default=25_216)
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--variants", default="0,1,2,3,4,5")
+    ap.add_argument("--variants", default="0")
     ap.add_argument("--chunks", default="2048")
     ap.add_argument("--child", default=None)
     a = ap.parse_args()
