@@ -80,7 +80,7 @@ struct Workspace {
   std::vector<bb_constraint> dedup_cons;   // host-side de-duplication of per-query descriptors (class mode)
   std::vector<int32_t> dedup_idx;
   // per-stream control block on the device (concurrent searches on other streams must not share these):
-  // bytes [0,64) statistics, [64,68) wave-barrier counter, [128,132) error / watchdog flag
+  // bytes [0,128) statistics, [128,132) wave-barrier counter, [192,196) error / watchdog flag
   unsigned char* ctl = nullptr;
   unsigned long long* stats() const { return reinterpret_cast<unsigned long long*>(ctl); }
   uint32_t* wave_counter() const { return reinterpret_cast<uint32_t*>(ctl + 128); }
