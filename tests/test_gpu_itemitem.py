@@ -102,3 +102,19 @@ def test_users_without_ratings_and_unrated_items(bb):
     s, i = eng.item_item_topk(indptr, indices, data, n_items, k)
     _check_rows(indptr, indices, data, n_items, k, s, i, np.arange(0, n_items, 7))
     eng.close()
+
+
+def test_massive_ties_overflow_the_survivor_buffer(bb):
+    """Every user rated every item with the same rating: all cosines are exactly 1, the selection bound admits the whole
+    row (2999 survivors > the 1024-key buffer), so pass C repeats until the row is drained; ties go to the lower id."""
+    n_items, n_users, k = 3000, 6, 24
+    indptr = np.arange(n_users + 1, dtype=np.int64) * n_items
+    indices = np.tile(np.arange(n_items, dtype=np.int32), n_users)
+    data = np.full(indices.shape[0], 2.0, dtype=np.float32)
+    eng = bb.ScoringEngine(1, 1, 0)
+    s, i = eng.item_item_topk(indptr, indices, data, n_items, k)
+    np.testing.assert_allclose(s, 1.0, rtol=1e-6)
+    for row in (0, 1, 7, 1500, 2999):
+        expect = [j for j in range(k + 1) if j != row][:k]
+        assert i[row].tolist() == expect, f"item {row}"
+    eng.close()
