@@ -292,7 +292,8 @@ __global__ void ii_bucket_scatter_kernel(const unsigned long long* __restrict__ 
 // units, counters[1] = number of hot items, counters[3] = integer accumulators, counters[7] = packed ratings.  Single block.
 __global__ void __launch_bounds__(1024)
 ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* __restrict__ order, int n, int chunk,
-                int* __restrict__ unit_off, int* __restrict__ hot_of, int4* __restrict__ unit_tab, int* __restrict__ counters) {
+                int* __restrict__ unit_off, int* __restrict__ hot_of, int4* __restrict__ unit_tab, int* __restrict__ counters,
+                int allow_packed) {
   if (threadIdx.x == 0) {
     // integer accumulators are exact while vmax^2 * (largest degree) stays below 2^31
     // (order[0] lies in the top floor(log2(degree + 1)) bucket: no degree exceeds twice its own + 1)
@@ -300,7 +301,7 @@ ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* _
     const long long vm = counters[5];
     counters[3] = (counters[4] == 0 && counters[6] == 1 && vm * vm * dmax < (1ll << 31)) ? 1 : 0;
     // packed ratings: (item | rating << 24) in one word per rating (written by ii_block_scatter_kernel)
-    counters[7] = (counters[3] != 0 && vm < 256 && n <= (1 << 24)) ? 1 : 0;
+    counters[7] = (allow_packed && counters[3] != 0 && vm < 256 && n <= (1 << 24)) ? 1 : 0;
   }
   // one scan carries both counts: units in the low word, hot items (more than one unit) in the high word
   const long long total = block_scan_1024(
@@ -418,8 +419,10 @@ __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i,
   const int n4 = (n + 3) >> 2;                     // (entries in [n, range) are never written: they stay zero)
   const uint4* acc4 = reinterpret_cast<const uint4*>(acc);
   const float4* inv4p = reinterpret_cast<const float4*>(inv_norm + j0);     // (j0 is a multiple of 32; padded allocation)
-  // pass A
+  // pass A.  Integer sums are never negative, so the cosine needs no sign test; the item's own entry is cleared by
+  // the one thread that meets its group.
   float best_c = 0.f;
+  const int self_q = (i >= j0 && i < j0 + n) ? ((i - j0) >> 2) : -1, self_u = (i - j0) & 3;
   for (int q = tid; q < n4; q += kThreads) {
     const uint4 w = acc4[q];
     if ((w.x | w.y | w.z | w.w) != 0u) {
@@ -429,8 +432,17 @@ __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i,
       float c[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float g = kInt ? static_cast<float>(wu[u]) : __uint_as_float(wu[u]);
-        c[u] = (g > 0.f && j0 + q * 4 + u != i) ? g * (inv_i * iv[u]) : 0.f;
+        if (kInt) {
+          c[u] = static_cast<float>(wu[u]) * (inv_i * iv[u]);
+        } else {
+          const float g = __uint_as_float(wu[u]);
+          c[u] = g > 0.f ? g * (inv_i * iv[u]) : 0.f;
+        }
+      }
+      if (q == self_q) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (u == self_u) c[u] = 0.f;
       }
       best_c = fmaxf(fmaxf(fmaxf(best_c, c[0]), fmaxf(c[1], c[2])), c[3]);
       reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
@@ -462,22 +474,28 @@ __device__ __forceinline__ void ii_select_smem(float* acc, int n, int j0, int i,
   }
   __syncthreads();
   thr_c = sh->thr_c;
-  // pass C
+  // pass C (one compare per entry: survivors are the positive entries >= T)
+  const float lim = fmaxf(thr_c, 1e-37f);
   while (true) {
     for (int q = tid; q < n4; q += kThreads) {
       const float4 w = reinterpret_cast<const float4*>(acc)[q];
       if (w.x != 0.f || w.y != 0.f || w.z != 0.f || w.w != 0.f) {
         float c[4] = {w.x, w.y, w.z, w.w};
+        if (c[0] >= lim || c[1] >= lim || c[2] >= lim || c[3] >= lim) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (c[u] >= thr_c && c[u] > 0.f) {
-            const int pos = atomicAdd(&sh->cnt, 1);
-            if (pos < kSelBuf) { buf[pos] = make_key(c[u], static_cast<uint32_t>(j0 + q * 4 + u)); c[u] = 0.f; }
-          } else {
-            c[u] = 0.f;
+          for (int u = 0; u < 4; ++u) {
+            bool keep = false;
+            if (c[u] >= lim) {
+              const int pos = atomicAdd(&sh->cnt, 1);
+              if (pos < kSelBuf) buf[pos] = make_key(c[u], static_cast<uint32_t>(j0 + q * 4 + u));
+              else keep = true;                      // buffer full: stays for the next round
+            }
+            if (!keep) c[u] = 0.f;
           }
+          reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
+        } else {
+          reinterpret_cast<float4*>(acc)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        reinterpret_cast<float4*>(acc)[q] = make_float4(c[0], c[1], c[2], c[3]);
       }
     }
     __syncthreads();
@@ -536,7 +554,7 @@ struct IIRaters {
   unsigned r;      // the rater's rating of item i (integer mode: the integer; else float bits)
 };
 
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, bool kOneRange>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
                      const uint32_t* __restrict__ packed, const long long* __restrict__ col_ptr, const int2* __restrict__ csc,
@@ -601,6 +619,7 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
         // several windows per round: the round's row reads are issued before the first shared-memory atomic needs one
         // (packed words: eight windows, 1 KB of row reads in flight per warp)
         if (use_packed) {
+          const uint32_t abase32 = static_cast<uint32_t>(abase);     // (packed words exist only while nnz < 2^31)
           for (int e0 = 0; e0 < total; e0 += 256) {
             uint32_t ww[8];
             unsigned rr[8];
@@ -612,15 +631,20 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
               const int r = rbase + __popc(ends & (0xffffffffu >> (31 - lane)));
               rbase += __popc(ends);
               const int e = w0 + lane;
-              const int64_t q = __shfl_sync(kFull, abase, r & 31) + e;
+              const uint32_t q = __shfl_sync(kFull, abase32, r & 31) + static_cast<uint32_t>(e);
               rr[x] = __shfl_sync(kFull, cur.r, r & 31);
               ww[x] = e < total ? __ldg(packed + q) : 0u;                 // (rating 0: adds nothing, skipped below)
             }
 #pragma unroll
             for (int x = 0; x < 8; ++x) {
-              const int j = static_cast<int>(ww[x] & 0xffffffu) - j0;
-              if (static_cast<unsigned>(j) < static_cast<unsigned>(j1 - j0) && (ww[x] >> 24) != 0u)
-                atomicAdd(reinterpret_cast<unsigned*>(acc) + j, rr[x] * (ww[x] >> 24));
+              const unsigned v = ww[x] >> 24;
+              if (kOneRange) {
+                if (v != 0u) atomicAdd(reinterpret_cast<unsigned*>(acc) + (ww[x] & 0xffffffu), rr[x] * v);
+              } else {
+                const int j = static_cast<int>(ww[x] & 0xffffffu) - j0;
+                if (static_cast<unsigned>(j) < static_cast<unsigned>(j1 - j0) && v != 0u)
+                  atomicAdd(reinterpret_cast<unsigned*>(acc) + j, rr[x] * v);
+              }
             }
           }
         } else {
@@ -794,7 +818,8 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
     ii_bucket_count_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters);
     ii_bucket_scan_kernel<<<1, 32, 0, stream>>>(counters, counters + 64);
     ii_bucket_scatter_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters + 64, order);
-    ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, unit_tab, counters + 128);
+    ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, unit_tab, counters + 128,
+                                            nnz < (1ll << 31) ? 1 : 0);
     ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
     launches += 5;
   };
@@ -839,18 +864,19 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
   range = (range + 31) / 32 * 32;
   const size_t smem = static_cast<size_t>(range) * 4 + side_bytes;
   const bool two = smem <= 112 * 1024;
-#define BB_II_LAUNCH(T, MB)                                                                                                \
+#define BB_II_LAUNCH(T, MB, ONE)                                                                                           \
   do {                                                                                                                     \
-    e = cudaFuncSetAttribute(ii_accumulate_kernel<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+    e = cudaFuncSetAttribute(ii_accumulate_kernel<T, MB, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
                              static_cast<int>(smem));                                                                      \
     if (e != cudaSuccess) return e;                                                                                        \
-    ii_accumulate_kernel<T, MB><<<sms * MB, T, smem, stream>>>(                                                            \
+    ii_accumulate_kernel<T, MB, ONE><<<sms * MB, T, smem, stream>>>(                                                       \
         indptr, indices, values, packed, col_ptr, csc, sq, unit_tab, counters + 128, n_items, range, chunk, k, max_hot,   \
         hot_rows, hot_done, counters + 130, out_scores, out_ids);                                                          \
   } while (0)
-  // (measured at config 3: 2 x 512 threads 2.81 ms, 2 x 768 3.7 ms, 2 x 1024 -- 32 registers, spills -- slower still)
-  if (two) BB_II_LAUNCH(512, 2);
-  else BB_II_LAUNCH(1024, 1);
+  // (measured at config 3: 2 x 512 threads beat 2 x 768 by 25% and 2 x 1024 -- 32 registers, spills -- by more)
+  if (two) BB_II_LAUNCH(512, 2, true);
+  else if (range >= n_items) BB_II_LAUNCH(1024, 1, true);
+  else BB_II_LAUNCH(1024, 1, false);
 #undef BB_II_LAUNCH
   ++launches;
   if (n_launches != nullptr) *n_launches = launches;
