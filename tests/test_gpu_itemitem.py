@@ -118,3 +118,17 @@ def test_massive_ties_overflow_the_survivor_buffer(bb):
         expect = [j for j in range(k + 1) if j != row][:k]
         assert i[row].tolist() == expect, f"item {row}"
     eng.close()
+
+
+def test_mid_sized_item_sets_one_cta_per_sm_and_large_k(bb):
+    """40k items: the accumulator (160 KB) leaves room for ONE CTA of 1024 threads per SM and still covers the catalog
+    in one range; k = 128 is the selector's capacity."""
+    n_items, n_users, k = 40_000, 80_000, 128
+    indptr, indices, data = synth.zipf_ratings_csr(n_users, n_items, 18, 21)
+    eng = bb.ScoringEngine(1, 1, 0)
+    s, i = eng.item_item_topk(indptr, indices, data, n_items, k)
+    deg = np.bincount(indices, minlength=n_items)
+    order = np.argsort(-deg)
+    rows = np.concatenate([order[:5], order[2000:2004], order[-4:]]).astype(int)
+    _check_rows(indptr, indices, data, n_items, k, s, i, rows)
+    eng.close()
