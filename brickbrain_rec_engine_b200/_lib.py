@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbrickscore.so")
+LIB_PATH = os.environ.get("BRICKSCORE_LIB") or os.path.join(HERE, "libbrickscore.so")   # (override: A/B runs of two builds)
 
 BB_OK = 0
 BB_ERR_INVALID = -22

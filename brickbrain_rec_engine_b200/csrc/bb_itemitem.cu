@@ -190,7 +190,8 @@ ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
   __syncthreads();
   int64_t u0, u1;
   sort_user_range(indptr, n_users, nnz, blockIdx.x, u0, u1);
-  const bool pack = counters[7] != 0;
+  const bool pack = counters[7] != 0, pack_csc = counters[8] != 0;
+  uint32_t* csc32 = reinterpret_cast<uint32_t*>(csc);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t ub = u0 + warp * 32; ub < u1; ub += kAccThreads) {
     const int64_t u = ub + lane;
@@ -232,7 +233,8 @@ ii_block_scatter_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
       for (int x = 0; x < 4; ++x) {
         if (c[x] < 0) continue;
         const uint32_t pos = atomicAdd(cursor + c[x], 1u);
-        csc[pos] = make_int2(static_cast<int32_t>(ub + owner[x]), __float_as_int(v[x]));
+        if (pack_csc) csc32[pos] = static_cast<uint32_t>(ub + owner[x]) | (static_cast<uint32_t>(v[x]) << 24);
+        else csc[pos] = make_int2(static_cast<int32_t>(ub + owner[x]), __float_as_int(v[x]));
         if (pack) packed[base + e0 + 32 * x + lane] = static_cast<uint32_t>(c[x]) | (static_cast<uint32_t>(v[x]) << 24);
       }
     }
@@ -293,7 +295,7 @@ __global__ void ii_bucket_scatter_kernel(const unsigned long long* __restrict__ 
 __global__ void __launch_bounds__(1024)
 ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* __restrict__ order, int n, int chunk,
                 int* __restrict__ unit_off, int* __restrict__ hot_of, int4* __restrict__ unit_tab, int* __restrict__ counters,
-                int allow_packed) {
+                int allow_packed, int allow_packed_users) {
   if (threadIdx.x == 0) {
     // integer accumulators are exact while vmax^2 * (largest degree) stays below 2^31
     // (order[0] lies in the top floor(log2(degree + 1)) bucket: no degree exceeds twice its own + 1)
@@ -302,6 +304,8 @@ ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* _
     counters[3] = (counters[4] == 0 && counters[6] == 1 && vm * vm * dmax < (1ll << 31)) ? 1 : 0;
     // packed ratings: (item | rating << 24) in one word per rating (written by ii_block_scatter_kernel)
     counters[7] = (allow_packed && counters[3] != 0 && vm < 256 && n <= (1 << 24)) ? 1 : 0;
+    // ... and (user | rating << 24) in one word per CSC entry while the users fit 24 bits: half the scatter's random stores
+    counters[8] = (counters[7] != 0 && allow_packed_users) ? 1 : 0;
   }
   // one scan carries both counts: units in the low word, hot items (more than one unit) in the high word
   const long long total = block_scan_1024(
@@ -571,7 +575,8 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_units = counters[0];
   const bool int_mode = counters[3] != 0;          // every rating is a small non-negative integer (set by ii_units_kernel)
-  const bool use_packed = counters[7] != 0;
+  const bool use_packed = counters[7] != 0, packed_csc = counters[8] != 0;
+  const uint32_t* csc32 = reinterpret_cast<const uint32_t*>(csc);
   for (int j = tid; j < range; j += kThreads) acc[j] = 0.f;
   if (tid == 0) s_unit[0] = atomicAdd(work_counter, 1);
   __syncthreads();
@@ -597,10 +602,18 @@ ii_accumulate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
         IIRaters f = {0, 0, 0u};
         const long long mine = (x0 + lane) * kWarps + warp;
         if (mine < n_raters) {
-          const int2 ur = __ldcs(csc + e_begin + mine);        // read once: evict first, the packed rows should stay in L2
-          f.r = int_mode ? static_cast<unsigned>(__int_as_float(ur.y)) : static_cast<unsigned>(ur.y);
-          f.p0 = __ldg(indptr + ur.x);
-          f.len = static_cast<int>(__ldg(indptr + ur.x + 1) - f.p0);
+          int user;
+          if (packed_csc) {                         // read once: evict first, the packed rows should stay in L2
+            const uint32_t w = __ldcs(csc32 + e_begin + mine);
+            user = static_cast<int>(w & 0xffffffu);
+            f.r = w >> 24;
+          } else {
+            const int2 ur = __ldcs(csc + e_begin + mine);
+            user = ur.x;
+            f.r = int_mode ? static_cast<unsigned>(__int_as_float(ur.y)) : static_cast<unsigned>(ur.y);
+          }
+          f.p0 = __ldg(indptr + user);
+          f.len = static_cast<int>(__ldg(indptr + user + 1) - f.p0);
         }
         return f;
       };
@@ -819,7 +832,7 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
     ii_bucket_scan_kernel<<<1, 32, 0, stream>>>(counters, counters + 64);
     ii_bucket_scatter_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(col_cnt, n_items, counters + 64, order);
     ii_units_kernel<<<1, 1024, 0, stream>>>(col_cnt, order, n_items, chunk, unit_off, hot_of, unit_tab, counters + 128,
-                                            nnz < (1ll << 31) ? 1 : 0);
+                                            nnz < (1ll << 31) ? 1 : 0, n_users <= (1ll << 24) ? 1 : 0);
     ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
     launches += 5;
   };
