@@ -125,25 +125,36 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         t_mark = getattr(self, "t_mark", 0.0)
-        for ts, l in self.lines:
-            if ts < t_mark:
-                continue
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+        def collect(t_lo, t_hi):
+            sm, mx, reasons = [], None, set()
+            for ts, l in self.lines:
+                if ts < t_lo or ts > t_hi:
+                    continue
+                f = [x.strip() for x in l.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        sm, mx, reasons = collect(t_mark, float("inf"))
+        out = {}
+        if not sm:
+            # a timed region shorter than the sampling period (config 2 / 3: a few ms): report the last second of the
+            # warm-up, which runs the same steps back to back
+            sm, mx, reasons = collect(t_mark - 1.0, t_mark)
+            out["window"] = "last second of the warm-up (the timed region is shorter than the 100 ms sampling period)"
+        out.update({"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)})
+        return out
 
 
 # ------------------------------------------------------------------------------------------ synthetic workload
@@ -424,8 +435,8 @@ def run_search_workload(args):
     if rank == 0:
         sampler.start()                 # nvidia-smi needs a moment to start: launch it before the warm-up
     # small catalogs finish a step in well under a millisecond: W such steps do not bring the SM clocks out of idle
-    # (measured: the first process of a session ran 15% slower than the next), so they get 300 more untimed steps
-    for i in range(args.warmup + (300 if flush_l2 else 0)):
+    # (measured: the first process of a session ran 15% slower than the next), so they get 600 more untimed steps
+    for i in range(args.warmup + (600 if flush_l2 else 0)):
         step_device(i)
     D.barrier()
     eng.set_profiling(True)
