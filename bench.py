@@ -829,8 +829,14 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sample_seconds"] * 1e3 * (args.batch / bs) * (args.n_items / ns),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"config4: {args.n_items} items x ({args.dim}+{args.cf_dim}), batch {args.batch}, per-query constraint sets, rated + self exclusion, top-{args.k}",
-                       "n_items": args.n_items, "batch": args.batch, "k": args.k},
+            # the GPU arm's workload (same catalog shape, batch, constraint mix, rated lists, k), computed in fp32 on the host
+            "config": {"workload": (f"config4: {args.n_items} items x ({args.dim}+{args.cf_dim}) fp32 catalog, batch {args.batch} hybrid queries "
+                                    f"(0.4 content cosine + 0.6 CF dot), per-query hard constraints (light/medium/heavy/none mix of the reference's "
+                                    f"scenarios; passed as 4 constraint sets + per-query index), per-user already-rated exclusion lists "
+                                    f"(48 ids each), self exclusion, top-{args.k}"),
+                       "n_items": args.n_items, "batch": args.batch, "k": args.k, "dim": args.dim, "cf_dim": args.cf_dim,
+                       "precision": "fp32", "constraint_form": "indexed", "parallelism": f"host threads x{cb.get('cores')}",
+                       "l2_policy": "n/a (CPU)"},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
