@@ -331,6 +331,65 @@ ii_units_kernel(const unsigned long long* __restrict__ col_cnt, const int32_t* _
   }
 }
 
+// Fused planning for catalogs that fit shared memory (the counting-sort path): column pointers, degree-bucket order
+// (hot columns first) and the unit table in ONE single-block launch over shared-memory copies of the counts.  The five
+// latency-sized launches it replaces (a scan, three bucket kernels, the unit scan: chains of dependent global loads in
+// single blocks) took 126 us of a 2.4 ms pass at config 3.
+__global__ void __launch_bounds__(1024)
+ii_plan_kernel(const unsigned long long* __restrict__ col_cnt, int n, int chunk, long long* __restrict__ col_ptr,
+               int4* __restrict__ unit_tab, int* __restrict__ counters, int allow_packed, int allow_packed_users) {
+  extern __shared__ __align__(16) unsigned char ii_smem[];
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(ii_smem);               // [n] column degrees (nnz < 2^32 on this path)
+  uint16_t* s_order = reinterpret_cast<uint16_t*>(s_cnt + n);           // [n] items by descending degree bucket (n <= 28,672)
+  __shared__ int s_bucket[64], s_pos[64];
+  const int t = threadIdx.x;
+  for (int i = t; i < n; i += 1024) s_cnt[i] = static_cast<uint32_t>(col_cnt[i]);
+  if (t < 64) s_bucket[t] = 0;
+  __syncthreads();
+  // column pointers
+  const long long total = block_scan_1024(
+      n, [&](int i) { return static_cast<long long>(s_cnt[i]); }, [&](int i, long long off, long long) { col_ptr[i] = off; });
+  if (t == 0) col_ptr[n] = total;
+  // items ordered by descending floor(log2(degree + 1)) (LPT balance; the order inside a bucket is arbitrary)
+  for (int i = t; i < n; i += 1024) atomicAdd(&s_bucket[63 - (31 - __clz(s_cnt[i] + 1u))], 1);
+  __syncthreads();
+  if (t == 0) {
+    int run = 0;
+    for (int b = 0; b < 64; ++b) { s_pos[b] = run; run += s_bucket[b]; }
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += 1024) s_order[atomicAdd(&s_pos[63 - (31 - __clz(s_cnt[i] + 1u))], 1)] = static_cast<uint16_t>(i);
+  __syncthreads();
+  if (t == 0) {
+    // integer accumulators are exact while vmax^2 * (largest degree) stays below 2^31
+    // (s_order[0] lies in the top bucket: no degree exceeds twice its own + 1)
+    const long long dmax = n > 0 ? 2 * (static_cast<long long>(s_cnt[s_order[0]]) + 1) : 1;
+    const long long vm = counters[5];
+    counters[3] = (counters[4] == 0 && counters[6] == 1 && vm * vm * dmax < (1ll << 31)) ? 1 : 0;
+    counters[7] = (allow_packed && counters[3] != 0 && vm < 256 && n <= (1 << 24)) ? 1 : 0;       // packed rating words
+    counters[8] = (counters[7] != 0 && allow_packed_users) ? 1 : 0;                               // packed CSC entries
+  }
+  // unit table: one scan carries both counts (units in the low word, hot items in the high word)
+  const long long tot = block_scan_1024(
+      n,
+      [&](int p) {
+        const long long d = s_cnt[s_order[p]];
+        const long long units = d <= chunk ? 1 : (d + chunk - 1) / chunk;
+        return units | (static_cast<long long>(units > 1) << 32);
+      },
+      [&](int p, long long off, long long v) {
+        const int item = s_order[p];
+        const int units = static_cast<int>(v & 0xffffffffll);
+        const int ru = static_cast<int>(off & 0xffffffffll), rh = static_cast<int>(off >> 32);
+        const int hot = units > 1 ? rh : -1;
+        for (int c = 0; c < units; ++c) unit_tab[ru + c] = make_int4(item, c, units, hot);
+      });
+  if (t == 0) {
+    counters[0] = static_cast<int>(tot & 0xffffffffll);
+    counters[1] = static_cast<int>(tot >> 32);
+  }
+}
+
 __global__ void ii_zero_hot_kernel(float* __restrict__ hot_rows, int* __restrict__ hot_done, const int* __restrict__ counters,
                                    int n_items, int max_hot) {
   const int n_hot = min(counters[1], max_hot);
@@ -847,11 +906,18 @@ cudaError_t launch_item_item(int64_t n_users, int n_items, const int64_t* indptr
     ii_block_hist_kernel<<<kSortCtas, kAccThreads, hist_smem, stream>>>(indptr, indices, values, n_users, nnz, n_items, block_hist, block_sq,
                                                                        counters + 128 + 4);
     ii_column_prefix_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(block_hist, block_sq, n_items, col_cnt, sq);
-    ii_scan_kernel<<<1, 1024, 0, stream>>>(col_cnt, n_items, col_ptr, nullptr);
-    plan_units();
+    {
+      const size_t plan_smem = static_cast<size_t>(n_items) * 6 + 16;
+      e = cudaFuncSetAttribute(ii_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan_smem));
+      if (e != cudaSuccess) return e;
+      ii_plan_kernel<<<1, 1024, plan_smem, stream>>>(col_cnt, n_items, chunk, col_ptr, unit_tab, counters + 128,
+                                                     nnz < (1ll << 31) ? 1 : 0, n_users <= (1ll << 24) ? 1 : 0);
+      ii_zero_hot_kernel<<<sms * 4, 256, 0, stream>>>(hot_rows, hot_done, counters + 128, n_items, max_hot);
+      launches += 2;
+    }
     ii_block_scatter_kernel<<<kSortCtas, kAccThreads, hist_smem, stream>>>(indptr, indices, values, n_users, nnz, n_items, block_hist,
                                                                           col_ptr, csc, counters + 128, packed);
-    launches += 4;
+    launches += 3;
   } else {
     if (nnz > 0) {
       ii_hist_kernel<<<static_cast<int>((nnz + 255) / 256), 256, 0, stream>>>(indices, values, nnz, col_cnt, sq);
