@@ -629,6 +629,7 @@ def run_item_item(args):
         t.append(e0.elapsed_time(e1))
     ms = float(np.mean(t))
     launches = eng.info()["launches"] - launches0
+    eng.item_item_topk(indptr, cols, vals, n_items, k)                # (untimed: first use allocates the staging buffers)
     t0 = time.perf_counter()
     for _ in range(max(1, args.steps // 4)):
         eng.item_item_topk(indptr, cols, vals, n_items, k)            # host CSR in, host lists out
