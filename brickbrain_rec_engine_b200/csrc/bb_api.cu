@@ -248,9 +248,9 @@ struct Stager {
     return big_h2d(dst, p, bytes);
   }
   static constexpr size_t kChunk = 8u << 20;
-  // one core copies pageable memory at ~3 GB/s on the GPU hosts: four cores keep the PCIe DMA of the previous chunk busy
+  // one core copies pageable memory at ~3-5 GB/s on the GPU hosts: eight cores keep the PCIe DMA of the previous chunk busy
   static void parallel_memcpy(unsigned char* dst, const unsigned char* src, size_t n) {
-    constexpr int kCopyThreads = 4;
+    constexpr int kCopyThreads = 8;
     const size_t part = (n / kCopyThreads + 4095) & ~static_cast<size_t>(4095);
     if (n < (1u << 20) || part == 0) { std::memcpy(dst, src, n); return; }
     std::thread helpers[kCopyThreads - 1];
