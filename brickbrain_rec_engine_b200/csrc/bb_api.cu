@@ -701,7 +701,9 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
   // ---- few distinct constraint sets (one shared by the batch, or an explicit constraint_index): evaluate each
   //      set once per item with the mask kernel (K3); the scan epilogue then masks a 32-item chunk of a row with
   //      one word of its set's bitmap
-  const int n_classes = (n_cons == 1 && B > 1) ? 1 : (q_cidx != nullptr ? n_cons : 0);
+  // (a single query with its own descriptor is a batch that shares one set: without the bitmap it took the per-row
+  // variant, which has no pilot seeds -- 0.24 ms per call instead of 0.13 ms at config 1 with a valid-set filter)
+  const int n_classes = n_cons == 1 ? 1 : (q_cidx != nullptr ? n_cons : 0);
   if (tc && dump == nullptr && n_classes >= 1 && n_classes <= 64) {
     const int64_t words = (h->cfg.n_items + 31) / 32;
     const size_t bm_bytes = static_cast<size_t>(n_classes) * words * sizeof(uint32_t);
