@@ -336,3 +336,32 @@ def test_exact_fp32_on_the_tensor_pipe_equals_the_ffma_scan(bb, k):
         else:
             assert flagged >= 10, ("tied data must exercise the fallback", flagged)
         eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16_rescore"])
+def test_pinned_host_buffers_skip_the_staging_mirror(bb, precision):
+    """Host arrays that already live in pinned memory (>= 64 KB) are DMA'd straight from / into the caller's buffers,
+    small or pageable ones are packed into the workspace's pinned mirror; a call may mix both.  Same results either way,
+    also when the same workspace alternates between the two kinds."""
+    import torch
+    n, d, f, b, k = 20_000, 384, 64, 600, 40
+    _, emb, itf, parts, year, theme = _catalog(n, d, f, 31)
+    eng = bb.ScoringEngine(n, d, f)
+    eng.load_catalog(emb=emb, item_factors=itf, num_parts=parts, year=year, theme_id=theme)
+    q = synth.embeddings(b, d, 32, "aniso")
+    u = synth.cf_factors(b, f, 33)
+    self_id = np.arange(b, dtype=np.int32)
+    cons = _mix_constraints(bb)
+    cidx = (np.arange(b) % 4).astype(np.int32)
+    kw = dict(w_content=0.4, w_cf=0.6, constraints=cons, constraint_index=cidx, precision=precision)
+    ref_s, ref_i = eng.search(k, q_emb=q, q_cf=u, self_id=self_id, **kw)               # pageable in, pageable out
+    pq, pu = torch.from_numpy(q).pin_memory(), torch.from_numpy(u).pin_memory()        # 900 KB / 150 KB: direct
+    ps = torch.from_numpy(self_id).pin_memory()                                        # 2.4 KB: mirror although pinned
+    out_s, out_i = torch.empty((b, k), dtype=torch.float32).pin_memory(), torch.empty((b, k), dtype=torch.int32).pin_memory()
+    for rep in range(3):
+        out_s.zero_(); out_i.zero_()
+        eng.search(k, q_emb=pq.numpy(), q_cf=pu.numpy(), self_id=ps.numpy(), out=(out_s.numpy(), out_i.numpy()), **kw)
+        assert np.array_equal(out_i.numpy(), ref_i) and np.array_equal(out_s.numpy(), ref_s), rep
+        s2, i2 = eng.search(k, q_emb=pq.numpy(), q_cf=u, self_id=self_id, **kw)         # mixed: pinned + pageable in one call
+        assert np.array_equal(i2, ref_i) and np.array_equal(s2, ref_s), rep
+    eng.close()
