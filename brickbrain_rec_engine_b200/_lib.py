@@ -120,6 +120,7 @@ PROTOTYPES = {
     "bb_search_sharded": (C.c_int, [_P, C.POINTER(bb_query_batch), C.c_int32, _P, _P, _P]),
     "bb_sharded_scatter": (C.c_int, [_P, C.POINTER(bb_query_batch), C.c_int32, _P]),
     "bb_sharded_collect": (C.c_int, [_P, _P, _P, _P]),
+    "bb_sharded_scatter_after": (C.c_int, [_P, C.POINTER(bb_query_batch), C.c_int32, _P, _P, _P]),
 }
 
 _lib = None

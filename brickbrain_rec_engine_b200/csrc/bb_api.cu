@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -139,6 +140,7 @@ struct bb_handle {
   bool pending_scatter = false;      // bb_sharded_scatter issued, bb_sharded_collect outstanding
   int pending_slice = 0, pending_parity = 0, pending_mine = 0, pending_k = 0;
   bool pending_l2 = false;
+  unsigned long long pending_expected = 0ull;   // arrivals the pending scatter's owner-side merge waits for
   unsigned long long* thr_shared() const { return reinterpret_cast<unsigned long long*>(comm); }
   std::atomic<uint32_t> epoch{0};          // private searches
   std::atomic<uint32_t> shared_epoch{0};   // collective searches (BB_Q_SHARE_THRESHOLDS): same sequence on all ranks
@@ -505,7 +507,7 @@ int defer_flag_check(bb_handle* h, Workspace* w, cudaStream_t stream) {
 // units, (pilot pass + threshold seeds,) run the scan.  On return `P` describes the candidate state.
 // `collective`: search of a row-sharded catalog whose ranks share thresholds through the communication block.
 int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, float* dump, cudaStream_t stream,
-             ScanParams& P, Plan& plan, bool collective) {
+             ScanParams& P, Plan& plan, bool collective, const std::function<int()>* before_scan = nullptr) {
   const int B = q->n_queries;
   const int prec = q->precision;
   // Exact fp32 on the tensor pipe: split-bf16 scan + exact re-score + proof of completeness (rows that cannot be proven
@@ -792,6 +794,13 @@ int run_scan(bb_handle* h, Workspace* w, const bb_query_batch* q, int k_sel, flo
     const int64_t pilot_items = static_cast<int64_t>(plan.pilot_tiles) * kTcTile;
     BB_CUDA(h, launch_seed_thresholds(PP, pilot_items < h->cfg.n_items ? pilot_items : h->cfg.n_items, stream));
     h->launches += 2;
+  }
+
+  // ---- (pipelined collective search) work that must precede this scan but not its prologue: the owner-side merge of
+  //      the PREVIOUS search waits for the peers' keys here, after this search's operands, masks and seeds are done
+  if (before_scan != nullptr) {
+    const int hrc = (*before_scan)();
+    if (hrc != BB_OK) return hrc;
   }
 
   // ---- scan
@@ -1445,7 +1454,26 @@ void comm_params(const bb_handle* h, int slice, int parity, CommParams& C) {
 
 // First half of a collective search: scan this shard against the union thresholds, merge, and deliver this rank's k
 // best keys of every query to the query's owner rank.  Enqueues only (never synchronizes).
-int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* stream_) {
+namespace {
+// launches the owner-side merge of the pending scatter into out_* (device or host memory)
+int launch_pending_collect(bb_handle* h, Workspace* w, float* out_scores, int32_t* out_ids, cudaStream_t stream, bool device_only) {
+  h->pending_scatter = false;
+  const int n_mine = h->pending_mine, k = h->pending_k;
+  const size_t n = static_cast<size_t>(n_mine > 0 ? n_mine : 1) * k;
+  OutPack o;
+  int rc = out_prepare(h, w, n, out_scores, out_ids, o);
+  if (rc != BB_OK) return rc;
+  if (device_only && o.host) return fail(h, BB_ERR_INVALID, "a pipelined collect needs device output buffers");
+  CommParams C;
+  comm_params(h, h->pending_slice, h->pending_parity, C);
+  BB_CUDA(h, launch_merge_inbox(C, n_mine, k, h->pending_expected, h->pending_l2, o.d_scores, o.d_ids, w->err_flag(), stream));
+  h->launches++;
+  if (device_only) return BB_OK;
+  if (n_mine == 0) return o.host ? check_device_flag(h, w, stream) : defer_flag_check(h, w, stream);
+  return out_finish(h, w, static_cast<size_t>(n_mine) * k, out_scores, out_ids, o, stream);
+}
+
+int sharded_scatter_impl(bb_handle* h, const bb_query_batch* q, int32_t k, float* prev_scores, int32_t* prev_ids, void* stream_) {
   if (h == nullptr) return BB_ERR_INVALID;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = device_guard(h);
@@ -1453,7 +1481,10 @@ int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* s
   rc = search_checks(h, q, k, q, q);
   if (rc != BB_OK) return rc;
   if (h->comm == nullptr || h->comm_world <= 1) return fail(h, BB_ERR_STATE, "sharded search needs bb_config.max_batch > 0 and bb_comm_import / bb_comm_link_local with world > 1");
-  if (h->pending_scatter) return fail(h, BB_ERR_STATE, "bb_sharded_scatter: the previous scatter was not collected");
+  const bool chain = prev_scores != nullptr || prev_ids != nullptr;
+  if (chain && (prev_scores == nullptr || prev_ids == nullptr || !h->pending_scatter))
+    return fail(h, BB_ERR_STATE, "bb_sharded_scatter_after needs both output buffers of a scatter that was not collected yet");
+  if (!chain && h->pending_scatter) return fail(h, BB_ERR_STATE, "bb_sharded_scatter: the previous scatter was not collected");
   const int B = q->n_queries, world = h->comm_world;
   const int b_pad = (B + 255) / 256 * 256;
   const int slice = (B + world - 1) / world;
@@ -1468,7 +1499,11 @@ int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* s
   ScanParams P;
   Plan plan;
   const int k_sel = k_select(k, rescore);
-  rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan, true);
+  // pipelined: the previous search's owner-side merge (which waits for the slowest peer's keys) is launched after THIS
+  // search's operand preparation, masks, pilot and seeds -- work that does not depend on the peers -- and before its scan;
+  // the two inbox halves stay safe because the merge still precedes this search's scan and scatter in stream order
+  const std::function<int()> collect_prev = [&]() { return launch_pending_collect(h, w, prev_scores, prev_ids, stream, true); };
+  rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan, true, chain ? &collect_prev : nullptr);
   if (rc != BB_OK) return rc;
   CommParams C;
   comm_params(h, slice, static_cast<int>(P.epoch & 1u), C);
@@ -1484,7 +1519,18 @@ int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* s
   h->pending_mine = n_mine;
   h->pending_k = k;
   h->pending_l2 = (q->flags & BB_Q_SCORES_AS_L2) != 0;
+  h->pending_expected = h->comm_expected[C.parity];
   return BB_OK;
+}
+}  // namespace
+
+int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* stream_) {
+  return sharded_scatter_impl(h, q, k, nullptr, nullptr, stream_);
+}
+int bb_sharded_scatter_after(bb_handle* h, const bb_query_batch* q, int32_t k, float* prev_out_scores, int32_t* prev_out_ids,
+                             void* stream_) {
+  if (prev_out_scores == nullptr || prev_out_ids == nullptr) return h != nullptr ? fail(h, BB_ERR_INVALID, "NULL argument") : BB_ERR_INVALID;
+  return sharded_scatter_impl(h, q, k, prev_out_scores, prev_out_ids, stream_);
 }
 
 // Second half: wait (on the device, bounded) until every rank's keys of this rank's query slice have arrived, merge
@@ -1499,18 +1545,7 @@ int bb_sharded_collect(bb_handle* h, float* out_scores, int32_t* out_ids, void* 
   Workspace* w = get_ws(h, stream);
   if (w == nullptr) return fail(h, BB_ERR_NOMEM, "workspace allocation failed");
   std::lock_guard<std::mutex> g(w->mu);
-  h->pending_scatter = false;
-  const int n_mine = h->pending_mine, k = h->pending_k;
-  const size_t n = static_cast<size_t>(n_mine > 0 ? n_mine : 1) * k;
-  OutPack o;
-  rc = out_prepare(h, w, n, out_scores, out_ids, o);
-  if (rc != BB_OK) return rc;
-  CommParams C;
-  comm_params(h, h->pending_slice, h->pending_parity, C);
-  BB_CUDA(h, launch_merge_inbox(C, n_mine, k, h->comm_expected[C.parity], h->pending_l2, o.d_scores, o.d_ids, w->err_flag(), stream));
-  h->launches++;
-  if (n_mine == 0) return o.host ? check_device_flag(h, w, stream) : defer_flag_check(h, w, stream);
-  return out_finish(h, w, static_cast<size_t>(n_mine) * k, out_scores, out_ids, o, stream);
+  return launch_pending_collect(h, w, out_scores, out_ids, stream, false);
 }
 
 int bb_search_sharded(bb_handle* h, const bb_query_batch* q, int32_t k, float* out_scores, int32_t* out_ids, void* stream_) {

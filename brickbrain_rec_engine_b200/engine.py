@@ -329,13 +329,24 @@ class ScoringEngine:
                             kwargs.get("w_cf", 0.0), kwargs.get("constraints"), kwargs.get("self_id"),
                             kwargs.get("precision", "fp32"), kwargs.get("as_l2", False), kwargs.get("constraint_index"),
                             kwargs.get("allow_bitmaps"), kwargs.get("excl_lists"), kwargs.get("prenormalized", False))
-        self._check(self._lib.bb_sharded_scatter(self._h, C.byref(qb), k, self._stream(stream)))
+        prev = kwargs.get("collect_previous_into")
+        if prev is not None:
+            # pipelined: the previous scatter's owner-side merge (into ``prev``: CUDA tensors [n_mine, k]) is launched
+            # inside this call, after this search's prologue and before its scan (``bb_sharded_scatter_after``)
+            ps, pi = a.ptr(prev[0], np.float32), a.ptr(prev[1], np.int32)
+            self._check(self._lib.bb_sharded_scatter_after(self._h, C.byref(qb), k, ps, pi, self._stream(stream)))
+        else:
+            self._check(self._lib.bb_sharded_scatter(self._h, C.byref(qb), k, self._stream(stream)))
         sl = -(-b // self.comm_world)
         return max(0, min(sl, b - self.comm_rank * sl))
 
-    def sharded_collect(self, k: int, n_mine: int, device: bool = False, stream=None):
-        """Second half: (scores, ids) [n_mine, k] of this rank's slice of the queries."""
+    def sharded_collect(self, k: int, n_mine: int, device: bool = False, stream=None, out=None):
+        """Second half: (scores, ids) [n_mine, k] of this rank's slice of the queries (``out``: CUDA tensors to fill)."""
         alloc = max(n_mine, 1)
+        if out is not None:
+            a = _Args()
+            self._check(self._lib.bb_sharded_collect(self._h, a.ptr(out[0], np.float32), a.ptr(out[1], np.int32), self._stream(stream)))
+            return out[0][:n_mine], out[1][:n_mine]
         if device:
             fs = torch.empty((alloc, k), dtype=torch.float32, device=f"cuda:{self.device}")
             fi = torch.empty((alloc, k), dtype=torch.int32, device=f"cuda:{self.device}")

@@ -184,6 +184,34 @@ class ShardedSearch:
             return self._deliver(ms, mi, nccl and host_call, host_out)
         return ms, mi
 
+    # ---- pipelined collective searches (p2p exchange, device inputs) ------------------------------------------
+    def search_pipelined(self, k: int, **kwargs):
+        """Back-to-back collective searches with the owner-side merge of search s launched inside search s+1 (after its
+        prologue, before its scan: ``bb_sharded_scatter_after``), so that waiting for the slowest peer's keys overlaps
+        work that does not depend on the peers.  Takes the keyword arguments of ``ScoringEngine.search`` (CUDA tensors)
+        and returns the (scores, ids) CUDA tensors of THIS search's slice of the queries -- their contents are complete
+        after the next ``search_pipelined`` call has been enqueued, or after ``flush()``."""
+        if self.world_size == 1 or self.exchange != "p2p":
+            s, i = self.search(k, result="slice", **kwargs)
+            return s, i
+        if kwargs.get("q_item") is not None:
+            kwargs = self._resolve_q_item(dict(kwargs))
+        prev = getattr(self, "_pending", None)
+        dev = f"cuda:{self.engine.device}"
+        n_mine = self.engine.sharded_scatter(k, collect_previous_into=None if prev is None else (prev[0], prev[1]), **kwargs)
+        alloc = max(n_mine, 1)
+        out = (torch.empty((alloc, k), dtype=torch.float32, device=dev), torch.empty((alloc, k), dtype=torch.int32, device=dev))
+        self._pending = (out[0], out[1], k, n_mine)
+        return out[0][:n_mine], out[1][:n_mine]
+
+    def flush(self):
+        """Finishes the last pipelined search (its merge is enqueued on the current stream)."""
+        prev = getattr(self, "_pending", None)
+        if prev is None:
+            return
+        self._pending = None
+        self.engine.sharded_collect(prev[2], prev[3], out=(prev[0], prev[1]))
+
     def _deliver(self, s, i, host_call: bool, host_out):
         if not host_call:
             return s, i

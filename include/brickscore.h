@@ -275,6 +275,13 @@ BB_API int bb_search_sharded(bb_handle* h, const bb_query_batch* q, int32_t k, f
  * enqueues work; collect waits on the device until all ranks' keys of this rank's slice have arrived. */
 BB_API int bb_sharded_scatter(bb_handle* h, const bb_query_batch* q, int32_t k, void* stream);
 BB_API int bb_sharded_collect(bb_handle* h, float* out_scores, int32_t* out_ids, void* stream);
+/* Pipelined form for back-to-back collective searches: scatters the NEXT search and launches the collect of the previous
+ * (not yet collected) scatter into prev_out_* (DEVICE memory, [n_mine x k] of that search) in between -- after the next
+ * search's operand preparation, masks and threshold seeds, before its scan.  The owner-side merge waits for the slowest
+ * peer's keys; here that wait overlaps work that does not depend on the peers.  prev_out_* are complete once the work
+ * enqueued by this call has run; the last search of a sequence is finished with bb_sharded_collect. */
+BB_API int bb_sharded_scatter_after(bb_handle* h, const bb_query_batch* q, int32_t k, float* prev_out_scores,
+                                    int32_t* prev_out_ids, void* stream);
 
 /*
  * Sparse (CSR ratings, fp32 values) x dense (fp64, row-major) product, Y[n_rows x L] = A[n_rows x n_cols] * X[n_cols x L]:

@@ -214,6 +214,66 @@ def test_collective_search_shards_on_one_gpu(bb, world):
         e.close()
 
 
+def test_pipelined_collective_searches_on_one_gpu(bb):
+    """bb_sharded_scatter_after: the owner-side merge of search s is launched inside search s+1 (after its prologue, before
+    its scan).  Four different batches back to back on three in-process shards: every search's slices must equal the
+    single-engine result of ITS batch (a stale or early merge would return another batch's rows), the inbox halves
+    alternate, the last search is finished by a plain collect."""
+    import torch
+    from brickbrain_rec_engine_b200.sharded import slice_bounds
+    world, n, d, f, b, k = 3, 150_000, 384, 64, 520, 60
+    themes, emb, itf, parts, year, theme = _catalog(n, d, f, 71)
+    cons = _mix_constraints(bb, 4)
+    cidx = (np.arange(b) % 4).astype(np.int32)
+    full = bb.ScoringEngine(n, d, f, max_batch=b)
+    full.load_catalog(emb=emb, item_factors=itf, num_parts=parts, year=year, theme_id=theme)
+    shards = []
+    for r in range(world):
+        lo, hi = bb.shard_bounds(n, world, r)
+        e = bb.ScoringEngine(hi - lo, d, f, id_offset=lo, max_batch=b)
+        e.load_catalog(emb=emb[lo:hi], item_factors=itf[lo:hi], num_parts=parts[lo:hi], year=year[lo:hi], theme_id=theme[lo:hi])
+        shards.append(e)
+    for r, e in enumerate(shards):
+        e.comm_link_local(r, shards)
+    batches = []
+    for step in range(4):
+        q = torch.from_numpy(synth.embeddings(b, d, 80 + step, "aniso") * 2.0).cuda()
+        u = torch.from_numpy(synth.cf_factors(b, f, 90 + step)).cuda()
+        batches.append(dict(q_emb=q, q_cf=u, w_content=0.4, w_cf=0.6, constraints=cons, constraint_index=cidx,
+                            precision="bf16_rescore" if step % 2 else "fp32"))
+    outs = []                                               # outs[step][r] = (scores, ids) CUDA tensors of shard r's slice
+    for step, kw in enumerate(batches):
+        cur = []
+        for r, e in enumerate(shards):
+            lo, hi = slice_bounds(b, world, r)
+            prev = None if step == 0 else outs[step - 1][r]
+            mine = e.sharded_scatter(k, collect_previous_into=prev, **kw)
+            assert mine == hi - lo
+            cur.append((torch.empty((hi - lo, k), dtype=torch.float32, device="cuda"),
+                        torch.empty((hi - lo, k), dtype=torch.int32, device="cuda")))
+        outs.append(cur)
+    for r, e in enumerate(shards):
+        lo, hi = slice_bounds(b, world, r)
+        e.sharded_collect(k, hi - lo, out=outs[-1][r])
+    torch.cuda.synchronize()
+    for step, kw in enumerate(batches):
+        fs, fi = full.search(k, **kw)
+        fs, fi = fs.cpu().numpy(), fi.cpu().numpy()
+        for r in range(world):
+            lo, hi = slice_bounds(b, world, r)
+            s, i = outs[step][r][0].cpu().numpy(), outs[step][r][1].cpu().numpy()
+            if kw["precision"] == "fp32":
+                _same_exact_ranking(fi[lo:hi], fs[lo:hi], i, s, f"step {step} shard {r}")
+            else:
+                rec = np.mean([len(set(i[x]) & set(fi[lo + x])) / k for x in range(hi - lo)])
+                assert rec >= 0.999, (step, r, rec)
+    # a chained scatter without a pending one is an error, not a hang
+    with pytest.raises(bb.BrickscoreError):
+        shards[0].sharded_scatter(k, collect_previous_into=outs[0][0], **batches[0])
+    for e in shards + [full]:
+        e.close()
+
+
 def test_twenty_threads_each_with_its_own_filter(bb):
     """tests/performance/production_scalability_test.py:247-281 drives 20 threads against the recommender: every
     request carries its own valid_set_filter and must never see another request's."""
