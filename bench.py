@@ -60,6 +60,9 @@ def parse():
     p.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                    help="N>1: p2p = union thresholds + owner inboxes over NVLink peer memory, fused into the kernels; "
                         "nccl = per-shard top-k, NCCL all-gather, merge kernel")
+    p.add_argument("--no-pipeline", action="store_true",
+                   help="N > 1, p2p exchange: collect every search before the next one starts (default: the owner-side merge of "
+                        "step s runs inside step s+1, after its prologue and before its scan)")
     p.add_argument("--no-rated", action="store_true", help="drop the per-user already-rated exclusion lists")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-check", action="store_true", help="skip the post-run correctness block")
@@ -412,14 +415,30 @@ def run_search_workload(args):
             kw["excl_lists"] = cv(qd["excl"])
         return kw
 
+    pipelined = world > 1 and exchange == "p2p" and not args.no_pipeline and not flush_l2
+    pipe_out = [(torch.empty((n_out, k), dtype=torch.float32, device=dev), torch.empty((n_out, k), dtype=torch.int32, device=dev))
+                for _ in range(2)] if pipelined else None
+    pipe_state = {"prev": None}
+
     def step_device(i):
         """Inputs resident in HBM; results stay on the device (world > 1: the rank's slice of the queries)."""
         kw = kwargs_of(devq[i & 1])
         if world == 1:
             return eng.search(k, out=(out_s, out_i), **kw)
+        if pipelined:
+            # back-to-back collective searches: step i's owner-side merge is launched inside step i+1 (after its prologue,
+            # before its scan); pipe_flush() finishes the last one -- K steps still run K scatters and K merges
+            eng.sharded_scatter(k, collect_previous_into=pipe_state["prev"], **kw)
+            pipe_state["prev"] = pipe_out[i & 1]
+            return pipe_out[i & 1]
         if exchange == "p2p":
             return eng.search(k, sharded=True, out=(out_s[:s_hi - s_lo], out_i[:s_hi - s_lo]), **kw)
         return ss.search(k, result="slice", **kw)
+
+    def pipe_flush():
+        if pipelined and pipe_state["prev"] is not None:
+            eng.sharded_collect(k, max(0, s_hi - s_lo), out=pipe_state["prev"])
+            pipe_state["prev"] = None
 
     def step_e2e(i):
         """The user-facing call with HOST buffers: pinned inputs in, results read back into host memory."""
@@ -438,6 +457,7 @@ def run_search_workload(args):
     # (measured: the first process of a session ran 15% slower than the next), so they get 600 more untimed steps
     for i in range(args.warmup + (600 if flush_l2 else 0)):
         step_device(i)
+    pipe_flush()
     D.barrier()
     eng.set_profiling(True)
     launches0 = eng.info()["launches"]
@@ -457,7 +477,8 @@ def run_search_workload(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            step_device(i)
+            last_out = step_device(i)
+        pipe_flush()
         e1.record()
         D.barrier()
         ms_total = D.max(e0.elapsed_time(e1))
@@ -469,6 +490,14 @@ def run_search_workload(args):
     ms_per_step = ms_total / args.steps
     value = b / (ms_per_step / 1e3)
     appends = info["last_appends"]
+    pipe_match = None
+    if pipelined:
+        # the last pipelined step against the same batch searched and collected in one call (fraction of identical rows)
+        ref_s, ref_i = eng.search(k, sharded=True, **kwargs_of(devq[(args.steps - 1) & 1]))
+        torch.cuda.synchronize()
+        rows = max(1, s_hi - s_lo)
+        same = (last_out[1][:rows].long().sort(dim=1).values == ref_i[:rows].long().sort(dim=1).values).all(dim=1).float().mean()
+        pipe_match = -D.max(-float(same.item()))
 
     # ---------------- end-to-end timing through the host-buffer API (`e2e`)
     for i in range(min(2, args.warmup)):
@@ -557,6 +586,7 @@ def run_search_workload(args):
                    "constraint_form": args.constraint_form,
                    "parallelism": f"row-sharded catalog x{world}" + ("" if world == 1 else
                                   (" + union thresholds and owner inboxes over NVLink peer memory (fused into the scan / merge kernels); each rank keeps the results of its query slice"
+                                   + ("; back-to-back steps are pipelined (the owner-side merge of step s runs inside step s+1, after its prologue and before its scan)" if pipelined else "")
                                    if exchange == "p2p" else " + NCCL all-gather top-k merge")),
                    "l2_policy": ("L2 flushed between steps (256 MB write), every step timed with its own CUDA events" if flush_l2 else
                                  f"catalog shard ({(hi - lo) * (d + f) * 2 / 1e9:.2f} GB bf16) is larger than L2 (126 MB); query batches alternate")},
@@ -573,6 +603,8 @@ def run_search_workload(args):
                      "appends_per_launch": int(appends)},
     }
     if check is not None:
+        if pipe_match is not None:
+            check["pipelined_rows_equal_to_plain_collective_search"] = pipe_match
         line["check"] = check
         line["recall_at_k"] = check["recall_at_k"]
         line["mask_violations"] = check["mask_violations"]

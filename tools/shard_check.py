@@ -6,7 +6,8 @@
 Every rank holds one shard; ``ShardedSearch`` must return exactly what ONE engine over the whole catalog returns, on
 the exact fp32 path bit for bit and with recall >= 0.999 on the bf16 + re-score path, through BOTH exchanges: ``p2p``
 (union thresholds over NVLink peer memory + owner inboxes, fused into the kernels) and ``nccl`` (all-gather + merge
-kernel), with host and device inputs, for ``q_emb`` and for ``q_item`` queries (resolved by the owner shard).  Prints
+kernel), with host and device inputs, plain and pipelined (``search_pipelined``), for ``q_emb`` and for ``q_item`` queries
+(resolved by the owner shard).  Prints
 how many candidates each shard's scan appended with / without the union thresholds.
 """
 import os
@@ -102,6 +103,14 @@ def main():
             if not same(prec, s, i, fs[s_lo:s_hi], fi[s_lo:s_hi], ref_i[s_lo:s_hi], ref_s[s_lo:s_hi]):
                 ok = False
                 print(f"[rank {rank}] MISMATCH {form} {prec} p2p device inputs", flush=True)
+            # pipelined: three searches back to back, each one's owner-side merge launched inside the next call
+            outs = [p2p.search_pipelined(k, precision=prec, **kw_dev) for _ in range(3)]
+            p2p.flush()
+            torch.cuda.synchronize()
+            for x, (s, i) in enumerate(outs):
+                if not same(prec, s, i, fs[s_lo:s_hi], fi[s_lo:s_hi], ref_i[s_lo:s_hi], ref_s[s_lo:s_hi]):
+                    ok = False
+                    print(f"[rank {rank}] MISMATCH {form} {prec} p2p pipelined search {x}", flush=True)
             # an unflagged search in between must not disturb the collective sequence
             if rank == 0:
                 part.search(k, precision=prec, **{kk: vv for kk, vv in kw.items() if kk != "q_item"}, **({"q_emb": q} if form == "q_item" else {}))
