@@ -118,6 +118,10 @@ np.testing.assert_allclose(np.asarray(s), rs, rtol=1e-5)
 s2, i2 = ss.search(k, result="slice", q_item=liked, q_cf=u, w_content=0.4, w_cf=0.6, self_id=liked, excl_lists=np.arange(b, dtype=np.int32))
 a, z = bb.slice_bounds(b, world, rank)
 assert np.array_equal(np.asarray(i2), rid[a:z])
+# without communication blocks (CPU / gloo) a pipelined search is a plain slice search and flush() has nothing to do
+s3, i3 = ss.search_pipelined(k, q_item=liked, q_cf=u, w_content=0.4, w_cf=0.6, self_id=liked, excl_lists=np.arange(b, dtype=np.int32))
+ss.flush()
+assert np.array_equal(np.asarray(i3), rid[a:z])
 try:
     ss.search(k, q_item=np.array([n + 5], dtype=np.int32))
     raise SystemExit("an id that no shard owns must be rejected")
