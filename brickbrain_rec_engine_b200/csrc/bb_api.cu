@@ -1503,8 +1503,13 @@ int sharded_scatter_impl(bb_handle* h, const bb_query_batch* q, int32_t k, float
   // search's operand preparation, masks, pilot and seeds -- work that does not depend on the peers -- and before its scan;
   // the two inbox halves stay safe because the merge still precedes this search's scan and scatter in stream order
   const std::function<int()> collect_prev = [&]() { return launch_pending_collect(h, w, prev_scores, prev_ids, stream, true); };
+  const int prev_parity = h->pending_parity;
   rc = run_scan(h, w, q, k_sel, nullptr, stream, P, plan, true, chain ? &collect_prev : nullptr);
   if (rc != BB_OK) return rc;
+  // chained searches must alternate between the two inbox halves: another collective search on this handle between them
+  // (an NCCL-exchange search that shares thresholds also advances the collective epoch) would make them collide
+  if (chain && static_cast<int>(P.epoch & 1u) == prev_parity)
+    return fail(h, BB_ERR_STATE, "bb_sharded_scatter_after: another collective search ran between the chained searches");
   CommParams C;
   comm_params(h, slice, static_cast<int>(P.epoch & 1u), C);
   BB_CUDA(h, launch_merge_emit(P, k, rescore ? k_rescore(k, k_sel) : 0, static_cast<const float*>(w->q_f32.p), h->cat_f32, false, nullptr, nullptr, &C, stream));
