@@ -1,5 +1,6 @@
-"""Item-item CF (config 3) variant probe: one workload, one child process per (BB_II_VARIANT, BB_II_CHUNK) pair.
-``python tools/ii_probe.py [--users 1000000] [--variants 0,1,2,3,4,5] [--chunks 2048,8192]``"""
+"""Item-item CF (config 3) probe: one workload, one child process per BB_II_CHUNK value (raters per work unit); set
+BRICKSCORE_LIB to time another build of the library on the same box.
+``python tools/ii_probe.py [--users 1000000] [--chunks 8192,16384]``"""
 import argparse
 import os
 import subprocess
@@ -58,8 +59,7 @@ if __name__ == "__main__":
     ap.add_argument("--n-items", type=int, default=25_216)
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--variants", default="0")
-    ap.add_argument("--chunks", default="2048")
+    ap.add_argument("--chunks", default="16384")
     ap.add_argument("--child", default=None)
     a = ap.parse_args()
     if a.child:
@@ -71,7 +71,6 @@ if __name__ == "__main__":
     np.savez(path, indptr=indptr, cols=cols, vals=vals)
     print(f"workload: {cols.shape[0]} ratings, generated in {time.time() - t0:.1f} s", flush=True)
     for c in a.chunks.split(","):
-        for v in a.variants.split(","):
-            env = dict(os.environ, BB_II_VARIANT=v, BB_II_CHUNK=c)
-            subprocess.run([sys.executable, os.path.abspath(__file__), "--child", path, "--n-items", str(a.n_items), "--k", str(a.k),
-                            "--steps", str(a.steps)], env=env, check=False)
+        env = dict(os.environ, BB_II_CHUNK=c)
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--child", path, "--n-items", str(a.n_items), "--k", str(a.k),
+                        "--steps", str(a.steps)], env=env, check=False)
