@@ -68,6 +68,7 @@ def _same_ranking(ref, got, what):
     for a, b in zip(ref, got):
         if a.set_num == b.set_num:
             assert (a.name, a.year, a.num_parts, a.theme_name) == (b.name, b.year, b.num_parts, b.theme_name), what
+            assert a.reasons == b.reasons and a.constraint_violations == b.constraint_violations, (what, a.reasons, b.reasons)
 
 
 def test_adopted_state(live, accelerated):
@@ -117,5 +118,8 @@ def test_hybrid_calls_match_the_live_reference(live, accelerated, case):
     if rc:
         assert sorted(a_res.valid_set_nums) == sorted(r_res.valid_set_nums), case
         assert len(a_res.applied_constraints) == len(r_res.applied_constraints)
+        for key in ("input_sets", "output_sets", "constraint_count"):
+            assert a_res.performance_stats[key] == r_res.performance_stats[key], (case, key)
+        assert len(a_res.violations) == len(r_res.violations)
     else:
         assert (a_res is None) == (r_res is None)
