@@ -64,6 +64,10 @@ class RecommendationRequest:
     must_be_available: bool = False
     exclude_owned: bool = False
     exclude_wishlisted: bool = False
+    # soft preferences: part of the reference's dataclass (recommendation_system.py:62-65), read by nothing on this path
+    preferred_themes: Optional[List[str]] = None
+    preferred_complexity: Optional[str] = None
+    budget_preference: Optional[float] = None
 
 
 def _size_category(num_parts: int) -> str:

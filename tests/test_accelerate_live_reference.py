@@ -123,3 +123,36 @@ def test_hybrid_calls_match_the_live_reference(live, accelerated, case):
         assert len(a_res.violations) == len(r_res.violations)
     else:
         assert (a_res is None) == (r_res is None)
+
+
+def test_request_objects_are_interchangeable(live, accelerated):
+    """``get_recommendations_from_request`` takes the reference's own ``RecommendationRequest`` (and the package's twin has
+    the same fields, soft preferences included)."""
+    import dataclasses
+    import ref_harness as rh
+    rs, _ = rh.load_reference()
+    ref, acc, sn = live["hyb"], accelerated, live["sn"]
+    kw = dict(user_id=7, liked_set=sn[120], top_k=6, pieces_max=1000, year_min=2005, preferred_themes=["City"], budget_preference=80.0)
+    assert [f.name for f in dataclasses.fields(bb.RecommendationRequest)] == [f.name for f in dataclasses.fields(rs.RecommendationRequest)]
+    r_recs, r_res = ref.get_recommendations_from_request(rs.RecommendationRequest(**kw))
+    a_recs, a_res = acc.get_recommendations_from_request(rs.RecommendationRequest(**kw))       # the reference's class
+    b_recs, b_res = acc.get_recommendations_from_request(bb.RecommendationRequest(**kw))       # the package's twin
+    _same_ranking(r_recs, a_recs, "request (reference class)")
+    _same_ranking(r_recs, b_recs, "request (package class)")
+    assert sorted(a_res.valid_set_nums) == sorted(r_res.valid_set_nums) == sorted(b_res.valid_set_nums)
+
+
+def test_public_types_have_the_reference_fields():
+    """Dataclass fields (names, order) and enum members of the adapter types equal the reference's; the package's
+    ``ConstraintResult`` only APPENDS its device bitmap."""
+    import dataclasses
+    import ref_harness as rh
+    rs, hcf = rh.load_reference()
+    names = lambda c: [f.name for f in dataclasses.fields(c)]
+    assert names(bb.RecommendationResult) == names(rs.RecommendationResult)
+    assert names(bb.RecommendationRequest) == names(rs.RecommendationRequest)
+    assert names(bb.HardConstraint) == names(hcf.HardConstraint)
+    assert names(bb.ConstraintViolation) == names(hcf.ConstraintViolation)
+    assert names(bb.ConstraintResult)[:len(names(hcf.ConstraintResult))] == names(hcf.ConstraintResult)
+    assert [(e.name, e.value) for e in bb.ConstraintType] == [(e.name, e.value) for e in hcf.ConstraintType]
+    assert [(e.name, e.value) for e in bb.ConstraintSeverity] == [(e.name, e.value) for e in hcf.ConstraintSeverity]
