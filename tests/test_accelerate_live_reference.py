@@ -156,3 +156,23 @@ def test_public_types_have_the_reference_fields():
     assert names(bb.ConstraintResult)[:len(names(hcf.ConstraintResult))] == names(hcf.ConstraintResult)
     assert [(e.name, e.value) for e in bb.ConstraintType] == [(e.name, e.value) for e in hcf.ConstraintType]
     assert [(e.name, e.value) for e in bb.ConstraintSeverity] == [(e.name, e.value) for e in hcf.ConstraintSeverity]
+
+
+def test_method_signatures_equal_the_reference():
+    """the seams callers already use keep their parameter names, order, kinds and defaults."""
+    import inspect
+    import ref_harness as rh
+    rs, hcf = rh.load_reference()
+    pairs = [(rs.ContentBasedRecommender.get_similar_sets, bb.ContentBasedRecommender.get_similar_sets),
+             (rs.CollaborativeFilteringRecommender.get_recommendations, bb.CollaborativeFilteringRecommender.get_recommendations),
+             (rs.CollaborativeFilteringRecommender.train_svd_model, bb.CollaborativeFilteringRecommender.train_svd_model),
+             (rs.HybridRecommender.get_recommendations, bb.HybridRecommender.get_recommendations),
+             (rs.HybridRecommender.get_recommendations_from_request, bb.HybridRecommender.get_recommendations_from_request),
+             (rs.HybridRecommender._combine_recommendations, bb.HybridRecommender._combine_recommendations),
+             (rs.HybridRecommender.set_weights, bb.HybridRecommender.set_weights),
+             (hcf.HardConstraintFilter.create_constraint_set, bb.HardConstraintFilter.create_constraint_set),
+             (hcf.HardConstraintFilter.apply_constraints, bb.HardConstraintFilter.apply_constraints)]
+    for r, o in pairs:
+        a = [(p.name, p.default, p.kind) for p in inspect.signature(r).parameters.values()]
+        b = [(p.name, p.default, p.kind) for p in inspect.signature(o).parameters.values()]
+        assert a == b, r.__qualname__
