@@ -121,6 +121,10 @@ def test_hybrid_calls_match_the_live_reference(live, accelerated, case):
         for key in ("input_sets", "output_sets", "constraint_count"):
             assert a_res.performance_stats[key] == r_res.performance_stats[key], (case, key)
         assert len(a_res.violations) == len(r_res.violations)
+        for rv, av in zip(r_res.violations, a_res.violations):          # hard_constraint_filter.py:534-637: counts, texts, advice
+            assert (av.constraint.constraint_type.value, av.constraint.value) == (rv.constraint.constraint_type.value, rv.constraint.value)
+            assert (av.violating_count, av.total_count, av.message) == (rv.violating_count, rv.total_count, rv.message), case
+            assert av.suggested_alternatives == rv.suggested_alternatives, case
     else:
         assert (a_res is None) == (r_res is None)
 
@@ -176,3 +180,19 @@ def test_method_signatures_equal_the_reference():
         a = [(p.name, p.default, p.kind) for p in inspect.signature(r).parameters.values()]
         b = [(p.name, p.default, p.kind) for p in inspect.signature(o).parameters.values()]
         assert a == b, r.__qualname__
+
+
+def test_violation_analysis_matches_the_live_reference(live, accelerated):
+    """``apply_constraints`` alone, on constraint sets that eliminate most or all of the catalog (the reference analyses
+    every constraint whose elimination rate is high: counts, message and suggested alternatives)."""
+    ref, acc = live["hyb"].constraint_filter, accelerated.constraint_filter
+    for kw in (dict(required_themes=["Nonexistent Theme"], pieces_max=100), dict(pieces_min=5000, price_max=5.0),
+               dict(year_min=2024, age_max=6), dict(max_complexity="simple", min_complexity="complex"),
+               dict(excluded_themes=["City"], must_be_available=True, pieces_max=60)):
+        r = ref.apply_constraints(ref.create_constraint_set(**kw))
+        a = acc.apply_constraints(acc.create_constraint_set(**kw))
+        assert sorted(a.valid_set_nums) == sorted(r.valid_set_nums), kw
+        assert len(a.violations) == len(r.violations), kw
+        for rv, av in zip(r.violations, a.violations):
+            assert (av.violating_count, av.total_count, av.message, av.suggested_alternatives) == \
+                   (rv.violating_count, rv.total_count, rv.message, rv.suggested_alternatives), kw
