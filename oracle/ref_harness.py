@@ -105,19 +105,24 @@ class _ShimCursor:
     def fetchone(self):
         return self._wrap(self._cur.fetchone())
 
+    @property
+    def description(self):          # pandas.read_sql on a DBAPI connection reads the column names from here
+        return self._cur.description
+
     def close(self):
         self._cur.close()
 
 
 class SqliteShimConnection:
-    """In-memory ``sets`` / ``themes`` / ``user_collections`` / ``user_wishlists``
+    """In-memory ``sets`` / ``themes`` / ``user_collections`` / ``user_wishlists`` / ``user_interactions``
     (column types as in src/db/rebrickable_schema.sql:38-46 and
     user_interaction_schema.sql)."""
 
     def __init__(self, set_nums: Sequence[str], names: Sequence[str], year: np.ndarray,
                  theme_id: np.ndarray, num_parts: np.ndarray, themes: Dict[int, str],
                  owned: Optional[Dict[int, Sequence[int]]] = None,
-                 wishlisted: Optional[Dict[int, Sequence[int]]] = None):
+                 wishlisted: Optional[Dict[int, Sequence[int]]] = None,
+                 ratings: Optional[Sequence[tuple]] = None):
         self.con = sqlite3.connect(":memory:")
         c = self.con.cursor()
         c.execute("CREATE TABLE themes (id INTEGER PRIMARY KEY, name TEXT NOT NULL, parent_id INTEGER)")
@@ -135,6 +140,10 @@ class SqliteShimConnection:
             if d:
                 c.executemany(f"INSERT INTO {table} VALUES (?,?)",
                               [(int(u), set_nums[int(i)]) for u, ids in d.items() for i in ids])
+        # user_interactions (user_interaction_schema.sql): the cold-start aggregates of recommendation_system.py:485-534
+        c.execute("CREATE TABLE user_interactions (user_id INTEGER, set_num TEXT, rating INTEGER)")
+        if ratings:
+            c.executemany("INSERT INTO user_interactions VALUES (?,?,?)", [(int(u), set_nums[int(i)], int(r)) for u, i, r in ratings])
         self.con.commit()
 
     def cursor(self, cursor_factory=None):

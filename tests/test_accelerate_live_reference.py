@@ -31,11 +31,13 @@ def live():
     frame = rh.make_set_frame(sn, [f"Set {i}" for i in range(n)], year, np.maximum(theme, 0), parts,
                               [themes.get(int(t), "Unknown") for t in theme])
     owned, wish = synth.user_lists(8, n, 30, seed=161), synth.user_lists(8, n, 20, seed=162)
-    con = rh.SqliteShimConnection(sn, [f"Set {i}" for i in range(n)], year, np.maximum(theme, 0), parts, themes, owned, wish)
-    content = rh.build_content(rs, None, frame, feat)
     ratings = synth.rating_matrix(n_users, n, seed=151)
     user_ids = list(range(1, n_users + 1))
-    cf = rh.build_cf(rs, None, frame, user_ids, ratings, None, None)
+    triples = [(user_ids[u], i, ratings[u, i]) for u in range(n_users) for i in np.nonzero(ratings[u] > 0)[0]]
+    con = rh.SqliteShimConnection(sn, [f"Set {i}" for i in range(n)], year, np.maximum(theme, 0), parts, themes, owned, wish,
+                                  ratings=triples)
+    content = rh.build_content(rs, con, frame, feat)
+    cf = rh.build_cf(rs, con, frame, user_ids, ratings, None, None)
     cf.svd_model = None
     cf.train_svd_model()                                     # the reference's own training (recommendation_system.py:368-409)
     hyb = rh.build_hybrid(rs, con, content, cf)
@@ -196,3 +198,20 @@ def test_violation_analysis_matches_the_live_reference(live, accelerated):
         for rv, av in zip(r.violations, a.violations):
             assert (av.violating_count, av.total_count, av.message, av.suggested_alternatives) == \
                    (rv.violating_count, rv.total_count, rv.message, rv.suggested_alternatives), kw
+
+
+def test_cold_start_matches_the_live_reference(live, accelerated):
+    """Unknown user: the reference answers from SQL aggregates over ``user_interactions`` (recommendation_system.py:485-534,
+    executed here on the SQLite shim); the adapter answers from the rating summary it adopted from the pivot table."""
+    import warnings
+    ref, acc, sn = live["hyb"].collaborative_recommender, accelerated.collaborative_recommender, live["sn"]
+    rated_any = np.nonzero((live["ratings"] > 0).sum(0) >= 3)[0]
+    valid = [sn[i] for i in rated_any[::2]] + [sn[i] for i in range(0, len(sn), 9)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                       # pandas: "only supports SQLAlchemy connectable"
+        for flt in (None, valid):
+            r = ref.get_recommendations(987654, 8, valid_set_filter=flt)
+            a = acc.get_recommendations(987654, 8, valid_set_filter=flt)
+            assert len(r) == len(a) > 0
+            assert [(x.set_num, x.score, x.reasons, x.name, x.year, x.num_parts, x.theme_name) for x in r] == \
+                   [(x.set_num, x.score, x.reasons, x.name, x.year, x.num_parts, x.theme_name) for x in a], flt
